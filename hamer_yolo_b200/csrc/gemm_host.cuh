@@ -1,0 +1,104 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map creation and kernel launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "gemm_tcgen05.cuh"
+
+namespace hm {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time (the build box has no driver; the .so must still link).
+inline PFN_tmapEncodeTiled get_tmap_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] (cols contiguous, row pitch = ld elements);
+// box = [box_rows, 64 cols] with the 128-byte swizzle.
+inline bool make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t ld, uint32_t box_rows) {
+    PFN_tmapEncodeTiled enc = get_tmap_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct GemmPlan {
+    int cta_group;  // 1 or 2
+    int bn;         // 128 or 256
+};
+
+template <int CTA_GROUP, int BN, int EPI>
+inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                                 int num_sms, cudaStream_t stream) {
+    using Cfg = GemmCfg<CTA_GROUP, BN>;
+    auto kern = gemm_bf16_tn_kernel<CTA_GROUP, BN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tile_m = GEMM_BM * CTA_GROUP;
+    const int tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BN);
+    int workers = num_sms / CTA_GROUP;
+    if (tiles < workers) workers = tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * CTA_GROUP);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTA_GROUP;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+}
+
+template <int CTA_GROUP, int BN>
+inline cudaError_t gemm_launch_e(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                                 const GemmParams& p, int num_sms, cudaStream_t s) {
+    switch (epi) {
+        case EPI_BIAS_BF16: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_BF16>(ta, tb, p, num_sms, s);
+        case EPI_BIAS_GELU_BF16: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_GELU_BF16>(ta, tb, p, num_sms, s);
+        case EPI_BIAS_RESID_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_RESID_F32>(ta, tb, p, num_sms, s);
+        case EPI_BIAS_POS_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_POS_F32>(ta, tb, p, num_sms, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// The W tensor map's box rows must equal BN / cta_group (see GemmCfg::B_ROWS).
+inline cudaError_t gemm_launch(GemmPlan plan, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                               const GemmParams& p, int num_sms, cudaStream_t s) {
+    if (p.K % GEMM_BK != 0 || p.N % plan.bn != 0) return cudaErrorInvalidValue;
+    if (plan.cta_group == 1 && plan.bn == 256) return gemm_launch_e<1, 256>(epi, ta, tb, p, num_sms, s);
+    if (plan.cta_group == 1 && plan.bn == 128) return gemm_launch_e<1, 128>(epi, ta, tb, p, num_sms, s);
+    if (plan.cta_group == 2 && plan.bn == 256) return gemm_launch_e<2, 256>(epi, ta, tb, p, num_sms, s);
+    if (plan.cta_group == 2 && plan.bn == 128) return gemm_launch_e<2, 128>(epi, ta, tb, p, num_sms, s);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace hm

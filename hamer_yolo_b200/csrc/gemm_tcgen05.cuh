@@ -1,0 +1,283 @@
+// bf16 x bf16 -> f32 GEMM for the ViT-H backbone:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+// Replaces every nn.Linear / the patch-embed Conv2d of the reference backbone
+// (hamer/hamer/models/backbones/vit.py:77-79 fc1/fc2, :104 qkv, :107 proj, :168 patch-embed conv),
+// which the reference runs through cuBLAS/MKL via ATen.
+//
+// sm_100a design
+//   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one lane),
+//     warps 2..9 = epilogue (TMEM -> registers -> global).
+//   * operands: TMA 128B-swizzled K-major tiles, BK = 64 (one swizzle atom per row), STAGES-deep
+//     mbarrier ring.
+//   * accumulators: fp32 in TMEM, two stages (2 x BN columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+//   * CTA_GROUP == 2: a CTA pair (cluster 2x1x1) computes a 256 x BN tile with UMMA M = 256; each
+//     CTA loads its own 128 rows of A and half (BN/2 rows) of W, the leader CTA issues the MMAs,
+//     tcgen05.commit multicasts the "slot free" / "accumulator full" signals to both CTAs.
+//   * epilogues (template EPI): bias -> bf16 | bias + exact-erf GELU -> bf16 |
+//     bias + residual add into the fp32 stream | bias + positional table -> fp32.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace hm {
+
+enum GemmEpilogue : int {
+    EPI_BIAS_BF16 = 0,       // out_bf16[m,n] = acc + bias[n]
+    EPI_BIAS_GELU_BF16 = 1,  // out_bf16[m,n] = gelu(acc + bias[n])
+    EPI_BIAS_RESID_F32 = 2,  // out_f32[m,n] += acc + bias[n]
+    EPI_BIAS_POS_F32 = 3,    // out_f32[m,n]  = acc + bias[n] + pos[(m % pos_rows), n]
+};
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;  // [N]
+    void* out;          // [M, ldo] bf16 or f32
+    int ldo;            // elements
+    const float* pos;   // [pos_rows, N] (EPI_BIAS_POS_F32)
+    int pos_rows;
+};
+
+constexpr int GEMM_BM = 128;  // rows per CTA (UMMA M = 128 * CTA_GROUP)
+constexpr int GEMM_BK = 64;   // 64 bf16 = 128 B = one swizzle atom row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+
+template <int CTA_GROUP, int BN>
+struct GemmCfg {
+    static constexpr int B_ROWS = BN / CTA_GROUP;  // rows of W each CTA loads per stage
+    static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr uint32_t B_BYTES = B_ROWS * GEMM_BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two >= 32)
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(TMEM_COLS == 512 || TMEM_COLS == 256 || TMEM_COLS == 128, "TMEM cols");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int CTA_GROUP, int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+    using Cfg = GemmCfg<CTA_GROUP, BN>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment. The dynamic-smem base offset is identical in
+    // both CTAs of a pair, so the aligned offsets match (required: the MMA uses one descriptor
+    // for both CTAs' shared memories).
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]  TMA bytes landed (leader CTA's is used)
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMAs that read the slot retired
+    uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       accumulator stage complete
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]       accumulator stage drained (leader's)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CTA_GROUP == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+
+    const int num_k = p.K / GEMM_BK;
+    const int n_blocks = p.N / BN;
+    const int tile_m = GEMM_BM * CTA_GROUP;
+    const int m_blocks = (p.M + tile_m - 1) / tile_m;
+    const int num_tiles = m_blocks * n_blocks;
+    const int worker = blockIdx.x / CTA_GROUP;
+    const int num_workers = gridDim.x / CTA_GROUP;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], GEMM_EPI_WARPS * CTA_GROUP);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<CTA_GROUP>(tmem_slot, Cfg::TMEM_COLS);
+    }
+    ptx::tc_fence_before();
+    if constexpr (CTA_GROUP == 2) ptx::cluster_sync_all(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+                const int m0 = m_blk * tile_m + (int)cta_rank * GEMM_BM;
+                const int n0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if constexpr (CTA_GROUP == 1) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage],
+                                         kb * GEMM_BK, m0);
+                        ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage],
+                                         kb * GEMM_BK, n0);
+                    } else {
+                        if (is_leader)
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        ptx::tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &tmap_a,
+                                             &full_bar[stage], kb * GEMM_BK, m0);
+                        ptx::tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES, &tmap_b,
+                                             &full_bar[stage], kb * GEMM_BK, n0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one lane) =====================
+        if (is_leader && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(GEMM_BM * CTA_GROUP, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t a_desc =
+                        ptx::make_smem_desc_k_sw128(ptx::smem_u32(smem_a + stage * Cfg::A_BYTES));
+                    const uint64_t b_desc =
+                        ptx::make_smem_desc_k_sw128(ptx::smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128 B swizzle atom
+                        const uint64_t koff = (uint64_t)((k * GEMM_UMMA_K * 2) >> 4);
+                        ptx::mma_f16<CTA_GROUP>(d_tmem, a_desc + koff, b_desc + koff, idesc,
+                                                (uint32_t)((kb | k) != 0));
+                    }
+                    if constexpr (CTA_GROUP == 1) ptx::mma_commit_1sm(&empty_bar[stage]);
+                    else ptx::mma_commit_2sm(&empty_bar[stage], 0x3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if constexpr (CTA_GROUP == 1) ptx::mma_commit_1sm(&tmem_full[acc]);
+                else ptx::mma_commit_2sm(&tmem_full[acc], 0x3);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int ew = warp - 2;
+        const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;               // which half of the BN columns
+        constexpr int COLS_PER_WARP = BN / 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int row = m_blk * tile_m + (int)cta_rank * GEMM_BM + quad * 32 + lane;
+            const int col0 = n_blk * BN + half * COLS_PER_WARP;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                    (uint32_t)(acc * BN + half * COLS_PER_WARP);
+#pragma unroll 1
+            for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_addr + (uint32_t)(c * 32), r);
+                ptx::tmem_ld_wait();
+                const int col = col0 + c * 32;
+                if (row < p.M) {
+                    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
+                    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                        __nv_bfloat16* out =
+                            reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v[8];
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const float4 b = __ldg(bias4 + j * 2 + q);
+                                v[q * 4 + 0] = __uint_as_float(r[j * 8 + q * 4 + 0]) + b.x;
+                                v[q * 4 + 1] = __uint_as_float(r[j * 8 + q * 4 + 1]) + b.y;
+                                v[q * 4 + 2] = __uint_as_float(r[j * 8 + q * 4 + 2]) + b.z;
+                                v[q * 4 + 3] = __uint_as_float(r[j * 8 + q * 4 + 3]) + b.w;
+                            }
+                            if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(v[0], v[1]);
+                            o.y = pack_bf16x2(v[2], v[3]);
+                            o.z = pack_bf16x2(v[4], v[5]);
+                            o.w = pack_bf16x2(v[6], v[7]);
+                            *reinterpret_cast<uint4*>(out + j * 8) = o;
+                        }
+                    } else {
+                        float* out = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
+                        const float* pos = nullptr;
+                        if constexpr (EPI == EPI_BIAS_POS_F32)
+                            pos = p.pos + (size_t)(row % p.pos_rows) * p.N + col;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(bias4 + j);
+                            float4 x;
+                            if constexpr (EPI == EPI_BIAS_RESID_F32)
+                                x = *reinterpret_cast<const float4*>(out + j * 4);
+                            else
+                                x = __ldg(reinterpret_cast<const float4*>(pos + j * 4));
+                            x.x += __uint_as_float(r[j * 4 + 0]) + b.x;
+                            x.y += __uint_as_float(r[j * 4 + 1]) + b.y;
+                            x.z += __uint_as_float(r[j * 4 + 2]) + b.z;
+                            x.w += __uint_as_float(r[j * 4 + 3]) + b.w;
+                            *reinterpret_cast<float4*>(out + j * 4) = x;
+                        }
+                    }
+                }
+            }
+            // this warp has finished reading the accumulator stage
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CTA_GROUP == 1) ptx::mbar_arrive(&tmem_empty[acc]);
+                else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    // ===================== teardown =====================
+    __syncwarp();  // reconverge the single-lane roles before the aligned barriers below
+    ptx::tc_fence_before();
+    if constexpr (CTA_GROUP == 2) ptx::cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<CTA_GROUP>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace hm
