@@ -26,8 +26,8 @@ inline PFN_tmapEncodeTiled get_tmap_encode() {
     return fn;
 }
 
-// Row-major bf16 matrix [rows, cols] (cols contiguous, row pitch = ld elements);
-// box = [box_rows, 64 cols] with the 128-byte swizzle.
+// Row-major 16-bit (fp16 or bf16 - TMA only moves bytes) matrix [rows, cols] (cols contiguous, row
+// pitch = ld elements); box = [box_rows, 64 cols] with the 128-byte swizzle.
 inline bool make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                               uint64_t ld, uint32_t box_rows) {
     PFN_tmapEncodeTiled enc = get_tmap_encode();

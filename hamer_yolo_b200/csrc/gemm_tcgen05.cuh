@@ -1,4 +1,9 @@
-// bf16 x bf16 -> f32 GEMM for the ViT-H backbone:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+// fp16 (activations) x bf16 (weights) -> f32 GEMM for the ViT-H backbone:
+//   C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+// Activations are fp16 rather than bf16 because the 0.5 mm / 1e-3 parity bar needs the 11-bit
+// mantissa (tests/tools/emulate_bf16.py: bf16 activations give 1.9e-3 on the rotation matrices,
+// fp16 3e-4); weights stay bf16 (the checkpoint values are bf16-representable); the products are
+// exact in the fp32 accumulator either way and the tensor-pipe rate is the same (kind::f16).
 //
 // Replaces every nn.Linear / the patch-embed Conv2d of the reference backbone
 // (hamer/hamer/models/backbones/vit.py:77-79 fc1/fc2, :104 qkv, :107 proj, :168 patch-embed conv),
@@ -18,14 +23,15 @@
 //     bias + residual add into the fp32 stream | bias + positional table -> fp32.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "ptx.cuh"
 
 namespace hm {
 
 enum GemmEpilogue : int {
-    EPI_BIAS_BF16 = 0,       // out_bf16[m,n] = acc + bias[n]
-    EPI_BIAS_GELU_BF16 = 1,  // out_bf16[m,n] = gelu(acc + bias[n])
+    EPI_BIAS_BF16 = 0,       // out_f16[m,n] = acc + bias[n]        (16-bit activation output)
+    EPI_BIAS_GELU_BF16 = 1,  // out_f16[m,n] = gelu(acc + bias[n])
     EPI_BIAS_RESID_F32 = 2,  // out_f32[m,n] += acc + bias[n]
     EPI_BIAS_POS_F32 = 3,    // out_f32[m,n]  = acc + bias[n] + pos[(m % pos_rows), n]
 };
@@ -33,7 +39,8 @@ enum GemmEpilogue : int {
 struct GemmParams {
     int M, N, K;
     const float* bias;  // [N]
-    void* out;          // [M, ldo] bf16 or f32
+    void* out;          // [M, ldo] fp16 or f32
+    uint32_t b_format;  // weight operand format: 1 = bf16 (default), 0 = fp16
     int ldo;            // elements
     const float* pos;   // [pos_rows, N] (EPI_BIAS_POS_F32)
     int pos_rows;
@@ -61,8 +68,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -154,7 +161,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA, one lane) =====================
         if (is_leader && lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(GEMM_BM * CTA_GROUP, BN);
+            const uint32_t idesc =
+                ptx::make_idesc_f16kind_f32(/*A fp16*/ 0, (int)p.b_format, GEMM_BM * CTA_GROUP, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -212,8 +220,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (row < p.M) {
                     const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
                     if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-                        __nv_bfloat16* out =
-                            reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col;
+                        __half* out = reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             float v[8];
@@ -230,10 +237,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
                             }
                             uint4 o;
-                            o.x = pack_bf16x2(v[0], v[1]);
-                            o.y = pack_bf16x2(v[2], v[3]);
-                            o.z = pack_bf16x2(v[4], v[5]);
-                            o.w = pack_bf16x2(v[6], v[7]);
+                            o.x = pack_act2(v[0], v[1]);
+                            o.y = pack_act2(v[2], v[3]);
+                            o.z = pack_act2(v[4], v[5]);
+                            o.w = pack_act2(v[6], v[7]);
                             *reinterpret_cast<uint4*>(out + j * 8) = o;
                         }
                     } else {

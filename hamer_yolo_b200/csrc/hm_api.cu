@@ -1,0 +1,845 @@
+// libhamer_b200.so - C ABI implementation (see include/hamer_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include "../../include/hamer_b200.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "crop_warp.cuh"
+#include "decoder_head.cuh"
+#include "elementwise.cuh"
+#include "gemm_host.cuh"
+#include "mano_lbs.cuh"
+
+using namespace hm;
+
+namespace {
+
+constexpr int TOK = 192;       // tokens per crop (16 x 12 patches)
+constexpr int DM = 1280;       // backbone width
+constexpr int DFF = 5120;
+constexpr int DEPTH = 32;
+constexpr int KPATCH = 1536;   // 2 x 768: [hi | lo] split of the fp32 pixels
+constexpr int HD = 1024;       // decoder width
+constexpr int HDEPTH = 6;
+constexpr int NREAD = 109;     // 96 pose6d + 10 betas + 3 cam
+
+std::string g_create_error;
+
+struct DevTensor {
+    float* f32 = nullptr;
+    __nv_bfloat16* bf16 = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+// raw pointers cached by hm_finalize_weights so the launch path does no name lookups
+struct BlockW {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_proj, *b_fc1, *b_fc2;
+    CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+};
+struct HeadLayerW {
+    const float *n0g, *n0b, *n1g, *n1b, *n2g, *n2b;
+    const float *w_sa_v, *w_sa_o, *b_sa_o;            // to_qkv rows 1024.. (v), to_out
+    const float *w_q, *w_kT, *w_v, *w_ca_o, *b_ca_o;  // to_q, transposed k, to_kv rows 512.. (v), to_out
+    const float *w1, *b1, *w2, *b2;                   // feed-forward
+};
+
+// fp32 -> 16-bit weight operand (fmt 1 = bf16, 0 = fp16), round to nearest even
+__global__ void f32_to_w16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, size_t n,
+                                  int fmt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (fmt == 1) {
+        const __nv_bfloat16 v = __float2bfloat16_rn(in[i]);
+        out[i] = *reinterpret_cast<const uint16_t*>(&v);
+    } else {
+        const __half v = __float2half_rn(in[i]);
+        out[i] = *reinterpret_cast<const uint16_t*>(&v);
+    }
+}
+
+}  // namespace
+
+struct hm_ctx {
+    int device = 0;
+    int num_sms = 0;
+    hm_config cfg{};
+    std::string err;
+    GemmPlan plan{2, 256};
+
+    std::map<std::string, DevTensor> w;   // every state-dict entry, on the device
+    bool finalized = false;
+    bool mano_set = false;
+
+    // fused tables built by hm_finalize_weights
+    __nv_bfloat16* w_patch2 = nullptr;    // [1280, 1536] = [W | W]
+    float* pos_tab = nullptr;             // [192, 1280] = pos[1:] + pos[0]
+    float* tok0 = nullptr;                // [1024] layer-0 decoder token
+    float* w_kT[HDEPTH] = {};             // [8][1280][64] transposed key projections
+    float* w_read = nullptr;              // [109, 1024]
+    float* b_read = nullptr;              // [109] bias + init_*
+    CUtensorMap tm_wpatch;
+    BlockW blk[DEPTH];
+    HeadLayerW hl[HDEPTH];
+    const float *b_patch = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+
+    // workspace (max_batch)
+    __half *patches = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;  // fp16 activations
+    uint32_t b_format = 1;   // weight operand format of the backbone GEMMs: 1 = bf16, 0 = fp16
+    float *x = nullptr, *feats = nullptr;
+    CUtensorMap tm_patches, tm_xn, tm_att, tm_h;
+    // decoder workspace
+    float *hx = nullptr, *hy = nullptr, *hv = nullptr, *hq = nullptr, *hu = nullptr, *hsc = nullptr,
+          *hpool = nullptr, *ho = nullptr, *hh = nullptr, *hraw = nullptr, *hrot = nullptr,
+          *hcamt = nullptr, *hbetas = nullptr, *hscratch = nullptr;
+
+    // MANO
+    ManoDevice mano{};
+    std::vector<void*> mano_allocs;
+
+    // preprocess
+    uint8_t* frame_dev = nullptr;
+    CropParams* crop_host = nullptr;   // pinned
+    CropParams* crop_dev = nullptr;
+    float* lut = nullptr;              // [3][256]
+    cudaEvent_t crop_event = nullptr;
+    bool crop_event_pending = false;
+
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int fail(hm_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define HM_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(ctx, HM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(hm_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e == cudaSuccess) {
+        c->allocs.push_back(q);
+        *p = reinterpret_cast<T*>(q);
+    }
+    return e;
+}
+
+const DevTensor* find(const hm_ctx* c, const std::string& name) {
+    auto it = c->w.find(name);
+    return it == c->w.end() ? nullptr : &it->second;
+}
+
+bool shape_is(const DevTensor* t, std::initializer_list<int64_t> s) {
+    if (!t || t->shape.size() != s.size()) return false;
+    size_t i = 0;
+    for (int64_t v : s) if (t->shape[i++] != v) return false;
+    return true;
+}
+
+std::string blk_name(int i, const char* tail) {
+    return "backbone.blocks." + std::to_string(i) + "." + tail;
+}
+std::string dec_name(int l, int sub, const char* tail) {
+    return "mano_head.transformer.transformer.layers." + std::to_string(l) + "." +
+           std::to_string(sub) + "." + tail;
+}
+
+// which state-dict matrices feed the bf16 tensor-core GEMMs
+bool is_backbone_matrix(const std::string& n) {
+    if (n.rfind("backbone.blocks.", 0) != 0) return false;
+    const char* tails[] = {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"};
+    for (const char* t : tails) {
+        size_t L = strlen(t);
+        if (n.size() > L && n.compare(n.size() - L, L, t) == 0) return true;
+    }
+    return false;
+}
+
+// ---- cv2.getAffineTransform for the reference's three axis-aligned point pairs ------------------
+// gen_trans_from_patch_cv (hamer/hamer/datasets/utils.py:82-129) with rot = 0, scale = 1; the 6x6
+// system is solved exactly like OpenCV's cv::solve(DECOMP_LU) (partial pivoting, plain double ops,
+// this file is compiled with -ffp-contract=off) so that M matches cv2 bit for bit.
+void lu_solve6(double A[6][6], double b[6]) {
+    const int m = 6;
+    for (int i = 0; i < m; ++i) {
+        int k = i;
+        for (int j = i + 1; j < m; ++j)
+            if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (k != i) {
+            for (int j = i; j < m; ++j) { double t = A[i][j]; A[i][j] = A[k][j]; A[k][j] = t; }
+            double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        const double d = -1 / A[i][i];
+        for (int j = i + 1; j < m; ++j) {
+            const double alpha = A[j][i] * d;
+            for (int c = i + 1; c < m; ++c) A[j][c] += alpha * A[i][c];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = m - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int c = i + 1; c < m; ++c) s -= A[i][c] * b[c];
+        b[i] = s / A[i][i];
+    }
+}
+
+void box_to_affine(const double* box, double* cx_out, double* cy_out, double* size_out, double M[6]) {
+    const double x1 = box[0], y1 = box[1], x2 = box[2], y2 = box[3];
+    const double cx = (x1 + x2) / 2.0, cy = (y1 + y2) / 2.0;               // infer.py:182-183
+    const double w = (2.5 * (x2 - x1) / 200.0) * 200, h = (2.5 * (y2 - y1) / 200.0) * 200;  // :193-199
+    double w_new, h_new;                                                    // expand_to_aspect_ratio
+    if (h / w < 256.0 / 192.0) { h_new = fmax(w * 256 / 192, h); w_new = w; }
+    else { h_new = h; w_new = fmax(h * 192 / 256, w); }
+    const double size = fmax(w_new, h_new);
+    const float half = (float)(size * 0.5);
+    const float s0x = (float)cx, s0y = (float)cy;
+    const float s1x = (float)(cx + 0.0), s1y = (float)(cy + (double)half);
+    const float s2x = (float)(cx + (double)half), s2y = (float)(cy + 0.0);
+    const double sx[3] = {s0x, s1x, s2x}, sy[3] = {s0y, s1y, s2y};
+    const double dx[3] = {128, 128, 256}, dy[3] = {128, 256, 128};
+    double A[6][6] = {}, b[6];
+    for (int i = 0; i < 3; ++i) {
+        A[2 * i][0] = sx[i]; A[2 * i][1] = sy[i]; A[2 * i][2] = 1;
+        A[2 * i + 1][3] = sx[i]; A[2 * i + 1][4] = sy[i]; A[2 * i + 1][5] = 1;
+        b[2 * i] = dx[i]; b[2 * i + 1] = dy[i];
+    }
+    lu_solve6(A, b);
+    for (int i = 0; i < 6; ++i) M[i] = b[i];
+    *cx_out = cx; *cy_out = cy; *size_out = size;
+}
+
+// cv::warpAffine's inversion of M (no WARP_INVERSE_MAP)
+void invert_affine(const double M[6], double out[6]) {
+    double m[6];
+    for (int i = 0; i < 6; ++i) m[i] = M[i];
+    double D = m[0] * m[4] - m[1] * m[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = m[4] * D, A22 = m[0] * D;
+    m[0] = A11; m[1] *= -D; m[3] *= -D; m[4] = A22;
+    const double b1 = -m[0] * m[2] - m[1] * m[5];
+    const double b2 = -m[3] * m[2] - m[4] * m[5];
+    m[2] = b1; m[5] = b2;
+    for (int i = 0; i < 6; ++i) out[i] = m[i];
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+template <int V, typename OutT>
+void launch_ln(const float* x, const float* g, const float* b, OutT* y, int rows, float eps,
+               cudaStream_t s) {
+    layernorm_kernel<V, OutT><<<(rows + 7) / 8, 256, 0, s>>>(x, g, b, y, rows, eps);
+}
+
+cudaError_t launch_skinny(int epi, const float* X, int ldx, long long x_bs, const float* W,
+                          long long w_bs, const float* bias, int bias_bs, float* Y, int ldy,
+                          long long y_bs, int B, int N, int K, int batch, float scale,
+                          cudaStream_t s) {
+    SkinnyParams p;
+    p.X = X; p.ldx = ldx; p.x_bs = x_bs; p.W = W; p.w_bs = w_bs; p.bias = bias; p.bias_bs = bias_bs;
+    p.Y = Y; p.ldy = ldy; p.y_bs = y_bs; p.B = B; p.N = N; p.K = K; p.scale = scale;
+    dim3 grid((N + SK_COLS - 1) / SK_COLS, (B + SK_ROWS - 1) / SK_ROWS, batch);
+    if (epi == SK_NONE) skinny_linear_kernel<SK_NONE><<<grid, SK_COLS * 32, 0, s>>>(p);
+    else if (epi == SK_GELU) skinny_linear_kernel<SK_GELU><<<grid, SK_COLS * 32, 0, s>>>(p);
+    else skinny_linear_kernel<SK_RESID><<<grid, SK_COLS * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+int run_gemm(hm_ctx* c, int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+             const float* bias, void* out, const float* pos, cudaStream_t s) {
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
+    p.b_format = c->b_format;
+    HM_CUDA(c, gemm_launch(c->plan, epi, ta, tb, p, c->num_sms, s));
+    return HM_OK;
+}
+
+int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStream_t s) {
+    const int M = B * TOK;
+    const float att_scale = 0.11180339887498948f * 1.4426950408889634f;   // 80^-0.5 * log2(e)
+    im2col_patch16_kernel<<<dim3(16, B), 256, 0, s>>>(img, c->patches, B);
+    int rc = run_gemm(c, EPI_BIAS_POS_F32, c->tm_patches, c->tm_wpatch, M, DM, KPATCH, c->b_patch,
+                      c->x, c->pos_tab, s);
+    if (rc) return rc;
+    for (int i = 0; i < DEPTH; ++i) {
+        const BlockW& w = c->blk[i];
+        launch_ln<10, __half>(c->x, w.ln1_g, w.ln1_b, c->xn, M, 1e-6f, s);
+        if ((rc = run_gemm(c, EPI_BIAS_BF16, c->tm_xn, w.tm_qkv, M, 3 * DM, DM, w.b_qkv, c->qkv, nullptr, s))) return rc;
+        vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(c->qkv, c->att, att_scale);
+        if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_att, w.tm_proj, M, DM, DM, w.b_proj, c->x, nullptr, s))) return rc;
+        launch_ln<10, __half>(c->x, w.ln2_g, w.ln2_b, c->xn, M, 1e-6f, s);
+        if ((rc = run_gemm(c, EPI_BIAS_GELU_BF16, c->tm_xn, w.tm_fc1, M, DFF, DM, w.b_fc1, c->hbuf, nullptr, s))) return rc;
+        if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_h, w.tm_fc2, M, DM, DFF, w.b_fc2, c->x, nullptr, s))) return rc;
+    }
+    launch_ln<10, float>(c->x, c->lnf_g, c->lnf_b, feats_out, M, 1e-6f, s);
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
+int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaStream_t s) {
+    head_init_token_kernel<<<(B * HD + 255) / 256, 256, 0, s>>>(c->tok0, c->hx, B);
+    const float scale = 0.125f;   // dim_head ** -0.5 = 64^-0.5
+    for (int l = 0; l < HDEPTH; ++l) {
+        const HeadLayerW& w = c->hl[l];
+        // self-attention on one token: x += to_out(W_v LN(x))
+        launch_ln<8, float>(c->hx, w.n0g, w.n0b, c->hy, B, 1e-5f, s);
+        HM_CUDA(c, launch_skinny(SK_NONE, c->hy, HD, 0, w.w_sa_v, 0, nullptr, 0, c->hv, 512, 0, B, 512, HD, 1, 1.f, s));
+        HM_CUDA(c, launch_skinny(SK_RESID, c->hv, 512, 0, w.w_sa_o, 0, w.b_sa_o, 0, c->hx, HD, 0, B, HD, 512, 1, 1.f, s));
+        // cross-attention against the 192 context tokens
+        launch_ln<8, float>(c->hx, w.n1g, w.n1b, c->hy, B, 1e-5f, s);
+        HM_CUDA(c, launch_skinny(SK_NONE, c->hy, HD, 0, w.w_q, 0, nullptr, 0, c->hq, 512, 0, B, 512, HD, 1, 1.f, s));
+        // u[b,h,:] = scale * W_k,h^T q[b,h,:]
+        HM_CUDA(c, launch_skinny(SK_NONE, c->hq, 512, 64, w.w_kT, (long long)DM * 64, nullptr, 0,
+                                 c->hu, 8 * DM, DM, B, DM, 64, 8, scale, s));
+        head_scores_kernel<<<dim3(6, B), 256, 0, s>>>(feats, c->hu, c->hsc);
+        head_pool_kernel<<<dim3(10, B), 128, 0, s>>>(feats, c->hsc, c->hpool);
+        // o[b, h*64 + d] = W_v,h pooled[b,h,:]
+        HM_CUDA(c, launch_skinny(SK_NONE, c->hpool, 8 * DM, DM, w.w_v, (long long)64 * DM, nullptr, 0,
+                                 c->ho, 512, 64, B, 64, DM, 8, 1.f, s));
+        HM_CUDA(c, launch_skinny(SK_RESID, c->ho, 512, 0, w.w_ca_o, 0, w.b_ca_o, 0, c->hx, HD, 0, B, HD, 512, 1, 1.f, s));
+        // feed-forward
+        launch_ln<8, float>(c->hx, w.n2g, w.n2b, c->hy, B, 1e-5f, s);
+        HM_CUDA(c, launch_skinny(SK_GELU, c->hy, HD, 0, w.w1, 0, w.b1, 0, c->hh, HD, 0, B, HD, HD, 1, 1.f, s));
+        HM_CUDA(c, launch_skinny(SK_RESID, c->hh, HD, 0, w.w2, 0, w.b2, 0, c->hx, HD, 0, B, HD, HD, 1, 1.f, s));
+    }
+    HM_CUDA(c, launch_skinny(SK_NONE, c->hx, HD, 0, c->w_read, 0, c->b_read, 0, c->hraw, NREAD, 0, B,
+                             NREAD, HD, 1, 1.f, s));
+    HeadOut ho;
+    // outputs the caller skipped are routed into scratch so the kernel stays branch-free
+    float* scratch = c->hscratch;
+    ho.global_orient = out && out->global_orient ? out->global_orient : scratch;
+    ho.hand_pose = out && out->hand_pose ? out->hand_pose : scratch + (size_t)B * 9;
+    ho.betas = c->hbetas;
+    ho.pred_cam = out && out->pred_cam ? out->pred_cam : scratch + (size_t)B * 144;
+    ho.pred_cam_t = c->hcamt;
+    ho.focal_length = out && out->focal_length ? out->focal_length : scratch + (size_t)B * 147;
+    ho.rotmats = c->hrot;
+    head_finalize_kernel<<<(B * 16 + 127) / 128, 128, 0, s>>>(c->hraw, ho, B, 5000.0f, 256.0f);
+    HM_CUDA(c, cudaGetLastError());
+    if (out && out->betas)
+        HM_CUDA(c, cudaMemcpyAsync(out->betas, c->hbetas, (size_t)B * 10 * 4, cudaMemcpyDeviceToDevice, s));
+    if (out && out->pred_cam_t)
+        HM_CUDA(c, cudaMemcpyAsync(out->pred_cam_t, c->hcamt, (size_t)B * 3 * 4, cudaMemcpyDeviceToDevice, s));
+    return HM_OK;
+}
+
+int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
+             float* verts, float* joints, float* kp2d, cudaStream_t s) {
+    LbsArgs a;
+    a.betas = betas; a.rotmats = rotmats; a.cam_t = cam_t; a.verts = verts; a.joints = joints;
+    a.kp2d = (cam_t != nullptr) ? kp2d : nullptr;
+    a.focal_over_size = 5000.0f / 256.0f;
+    a.B = B;
+    mano_lbs_kernel<<<(B + LBS_HANDS - 1) / LBS_HANDS, LBS_THREADS, sizeof(LbsSmem), s>>>(c->mano, a);
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
+int check_ready(hm_ctx* c, int B, bool need_weights, bool need_mano) {
+    if (!c) return HM_ERR_INVALID;
+    if (B <= 0) return fail(c, HM_ERR_INVALID, "batch size must be positive");
+    if (need_weights && !c->finalized) return fail(c, HM_ERR_STATE, "weights not finalized (hm_finalize_weights)");
+    if (need_weights && B > c->cfg.max_batch)
+        return fail(c, HM_ERR_INVALID, "B = " + std::to_string(B) + " exceeds hm_config.max_batch = " +
+                                           std::to_string(c->cfg.max_batch));
+    if (need_mano && !c->mano_set) return fail(c, HM_ERR_STATE, "MANO tables not set (hm_set_mano)");
+    return HM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* hm_version(void) { return "hamer_b200 0.1 (sm_100a; tcgen05/TMA GEMM, fp32 head, fused MANO LBS)"; }
+
+const char* hm_last_error(const hm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
+    if (!out || !cfg || cfg->max_batch <= 0) return fail(nullptr, HM_ERR_INVALID, "hm_create: bad arguments");
+    *out = nullptr;
+    hm_ctx* c = new hm_ctx();
+    c->device = device_ordinal;
+    c->cfg = *cfg;
+    auto bail = [&](int code, const std::string& m) { g_create_error = m; hm_destroy(c); return code; };
+    cudaError_t e = cudaSetDevice(device_ordinal);
+    if (e != cudaSuccess) return bail(HM_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device_ordinal);
+    if (e != cudaSuccess) return bail(HM_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10) return bail(HM_ERR_UNSUPPORTED, "hamer_b200 needs an sm_100 (B200) device, found sm_" +
+                                                              std::to_string(prop.major) + std::to_string(prop.minor));
+    c->num_sms = prop.multiProcessorCount;
+    c->plan.cta_group = (cfg->gemm_cta_group == 1) ? 1 : 2;
+    c->plan.bn = 256;
+    c->b_format = cfg->weights_f16 ? 0u : 1u;
+    if (!get_tmap_encode()) return bail(HM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+
+    const size_t Mmax = (size_t)cfg->max_batch * TOK, Bm = (size_t)cfg->max_batch;
+#define CA(call) do { if ((call) != cudaSuccess) return bail(HM_ERR_CUDA, "workspace allocation failed: " #call); } while (0)
+    CA(dev_alloc(c, &c->patches, Mmax * KPATCH));
+    CA(dev_alloc(c, &c->xn, Mmax * DM));
+    CA(dev_alloc(c, &c->qkv, Mmax * 3 * DM));
+    CA(dev_alloc(c, &c->att, Mmax * DM));
+    CA(dev_alloc(c, &c->hbuf, Mmax * DFF));
+    CA(dev_alloc(c, &c->x, Mmax * DM));
+    CA(dev_alloc(c, &c->feats, Mmax * DM));
+    CA(dev_alloc(c, &c->hx, Bm * HD));
+    CA(dev_alloc(c, &c->hy, Bm * HD));
+    CA(dev_alloc(c, &c->hv, Bm * 512));
+    CA(dev_alloc(c, &c->hq, Bm * 512));
+    CA(dev_alloc(c, &c->hu, Bm * 8 * DM));
+    CA(dev_alloc(c, &c->hsc, Bm * 8 * TOK));
+    CA(dev_alloc(c, &c->hpool, Bm * 8 * DM));
+    CA(dev_alloc(c, &c->ho, Bm * 512));
+    CA(dev_alloc(c, &c->hh, Bm * HD));
+    CA(dev_alloc(c, &c->hraw, Bm * NREAD));
+    CA(dev_alloc(c, &c->hrot, Bm * 144));
+    CA(dev_alloc(c, &c->hcamt, Bm * 3));
+    CA(dev_alloc(c, &c->hbetas, Bm * 10));
+    CA(dev_alloc(c, &c->hscratch, Bm * 160));
+    CA(dev_alloc(c, &c->crop_dev, Bm));
+    CA(dev_alloc(c, &c->lut, (size_t)768));
+    if (cfg->max_frame_bytes > 0) CA(dev_alloc(c, &c->frame_dev, (size_t)cfg->max_frame_bytes));
+    CA(cudaMallocHost(reinterpret_cast<void**>(&c->crop_host), Bm * sizeof(CropParams)));
+    CA(cudaEventCreateWithFlags(&c->crop_event, cudaEventDisableTiming));
+    // the workspace is read by TMA beyond the live rows of a partial tile: keep it finite
+    CA(cudaMemset(c->patches, 0, Mmax * KPATCH * 2));
+    CA(cudaMemset(c->xn, 0, Mmax * DM * 2));
+    CA(cudaMemset(c->att, 0, Mmax * DM * 2));
+    CA(cudaMemset(c->hbuf, 0, Mmax * DFF * 2));
+#undef CA
+    // normalisation LUT with the reference's float32 arithmetic (infer.py:145-146, 235-238)
+    {
+        const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+        float lut[768];
+        for (int ch = 0; ch < 3; ++ch) {
+            const float m = (float)(255. * mean[ch]), sd = (float)(255. * stdv[ch]);
+            for (int v = 0; v < 256; ++v) lut[ch * 256 + v] = ((float)v - m) / sd;
+        }
+        if (cudaMemcpy(c->lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(HM_ERR_CUDA, "LUT upload failed");
+    }
+    bool ok = make_tmap_bf16_2d(&c->tm_patches, c->patches, Mmax, KPATCH, KPATCH, GEMM_BM) &&
+              make_tmap_bf16_2d(&c->tm_xn, c->xn, Mmax, DM, DM, GEMM_BM) &&
+              make_tmap_bf16_2d(&c->tm_att, c->att, Mmax, DM, DM, GEMM_BM) &&
+              make_tmap_bf16_2d(&c->tm_h, c->hbuf, Mmax, DFF, DFF, GEMM_BM);
+    if (!ok) return bail(HM_ERR_CUDA, "activation tensor-map encoding failed");
+    if (cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ATT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(mano_lbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(LbsSmem)) != cudaSuccess)
+        return bail(HM_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
+    *out = c;
+    return HM_OK;
+}
+
+void hm_destroy(hm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->allocs) cudaFree(p);
+    for (void* p : c->mano_allocs) cudaFree(p);
+    for (auto& kv : c->w) { cudaFree(kv.second.f32); cudaFree(kv.second.bf16); }
+    if (c->crop_host) cudaFreeHost(c->crop_host);
+    if (c->crop_event) cudaEventDestroy(c->crop_event);
+    delete c;
+}
+
+int hm_set_weight(hm_ctx* c, const char* name, const float* data, const int64_t* shape, int ndim) {
+    if (!c || !name || !data || !shape || ndim < 1 || ndim > 4) return fail(c, HM_ERR_INVALID, "hm_set_weight: bad arguments");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    DevTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
+    const std::string key(name);
+    auto old = c->w.find(key);
+    if (old != c->w.end()) { cudaFree(old->second.f32); cudaFree(old->second.bf16); c->w.erase(old); }
+    HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.f32), t.numel * 4));
+    HM_CUDA(c, cudaMemcpy(t.f32, data, t.numel * 4, cudaMemcpyHostToDevice));
+    if (is_backbone_matrix(key)) {
+        // tensor-core operand: keep only the bf16 copy
+        HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.bf16), t.numel * 2));
+        f32_to_w16_kernel<<<(unsigned)((t.numel + 255) / 256), 256>>>(
+            t.f32, reinterpret_cast<uint16_t*>(t.bf16), t.numel, (int)c->b_format);
+        HM_CUDA(c, cudaDeviceSynchronize());
+        cudaFree(t.f32);
+        t.f32 = nullptr;
+    }
+    c->w[key] = t;
+    c->finalized = false;
+    return HM_OK;
+}
+
+int hm_finalize_weights(hm_ctx* c) {
+    if (!c) return HM_ERR_INVALID;
+    HM_CUDA(c, cudaSetDevice(c->device));
+    // ---- presence / shape checks -----------------------------------------------------------
+    auto need = [&](const std::string& n, std::initializer_list<int64_t> s) -> bool {
+        if (!shape_is(find(c, n), s)) { c->err = "missing or mis-shaped weight: " + n; return false; }
+        return true;
+    };
+    if (!need("backbone.patch_embed.proj.weight", {DM, 3, 16, 16}) || !need("backbone.patch_embed.proj.bias", {DM}) ||
+        !need("backbone.pos_embed", {1, TOK + 1, DM}) || !need("backbone.last_norm.weight", {DM}) ||
+        !need("backbone.last_norm.bias", {DM}))
+        return HM_ERR_INVALID;
+    for (int i = 0; i < DEPTH; ++i) {
+        if (!need(blk_name(i, "norm1.weight"), {DM}) || !need(blk_name(i, "norm1.bias"), {DM}) ||
+            !need(blk_name(i, "norm2.weight"), {DM}) || !need(blk_name(i, "norm2.bias"), {DM}) ||
+            !need(blk_name(i, "attn.qkv.weight"), {3 * DM, DM}) || !need(blk_name(i, "attn.qkv.bias"), {3 * DM}) ||
+            !need(blk_name(i, "attn.proj.weight"), {DM, DM}) || !need(blk_name(i, "attn.proj.bias"), {DM}) ||
+            !need(blk_name(i, "mlp.fc1.weight"), {DFF, DM}) || !need(blk_name(i, "mlp.fc1.bias"), {DFF}) ||
+            !need(blk_name(i, "mlp.fc2.weight"), {DM, DFF}) || !need(blk_name(i, "mlp.fc2.bias"), {DM}))
+            return HM_ERR_INVALID;
+    }
+    if (!need("mano_head.transformer.pos_embedding", {1, 1, HD}) ||
+        !need("mano_head.transformer.to_token_embedding.weight", {HD, 1}) ||
+        !need("mano_head.transformer.to_token_embedding.bias", {HD}) ||
+        !need("mano_head.decpose.weight", {96, HD}) || !need("mano_head.decpose.bias", {96}) ||
+        !need("mano_head.decshape.weight", {10, HD}) || !need("mano_head.decshape.bias", {10}) ||
+        !need("mano_head.deccam.weight", {3, HD}) || !need("mano_head.deccam.bias", {3}) ||
+        !need("mano_head.init_hand_pose", {1, 96}) || !need("mano_head.init_betas", {1, 10}) ||
+        !need("mano_head.init_cam", {1, 3}))
+        return HM_ERR_INVALID;
+    for (int l = 0; l < HDEPTH; ++l) {
+        for (int sub = 0; sub < 3; ++sub)
+            if (!need(dec_name(l, sub, "norm.weight"), {HD}) || !need(dec_name(l, sub, "norm.bias"), {HD}))
+                return HM_ERR_INVALID;
+        if (!need(dec_name(l, 0, "fn.to_qkv.weight"), {1536, HD}) ||
+            !need(dec_name(l, 0, "fn.to_out.0.weight"), {HD, 512}) || !need(dec_name(l, 0, "fn.to_out.0.bias"), {HD}) ||
+            !need(dec_name(l, 1, "fn.to_kv.weight"), {1024, DM}) || !need(dec_name(l, 1, "fn.to_q.weight"), {512, HD}) ||
+            !need(dec_name(l, 1, "fn.to_out.0.weight"), {HD, 512}) || !need(dec_name(l, 1, "fn.to_out.0.bias"), {HD}) ||
+            !need(dec_name(l, 2, "fn.net.0.weight"), {HD, HD}) || !need(dec_name(l, 2, "fn.net.0.bias"), {HD}) ||
+            !need(dec_name(l, 2, "fn.net.3.weight"), {HD, HD}) || !need(dec_name(l, 2, "fn.net.3.bias"), {HD}))
+            return HM_ERR_INVALID;
+    }
+    // ---- fused tables (built on the host from device copies; one-time cost) -----------------
+    auto fetch = [&](const std::string& n, std::vector<float>& h) -> cudaError_t {
+        const DevTensor* t = find(c, n);
+        h.resize(t->numel);
+        return cudaMemcpy(h.data(), t->f32, t->numel * 4, cudaMemcpyDeviceToHost);
+    };
+    std::vector<float> h, h2, h3;
+    if (!c->w_patch2) {
+        HM_CUDA(c, dev_alloc(c, &c->w_patch2, (size_t)DM * KPATCH));
+        HM_CUDA(c, dev_alloc(c, &c->pos_tab, (size_t)TOK * DM));
+        HM_CUDA(c, dev_alloc(c, &c->tok0, (size_t)HD));
+        HM_CUDA(c, dev_alloc(c, &c->w_read, (size_t)NREAD * HD));
+        HM_CUDA(c, dev_alloc(c, &c->b_read, (size_t)NREAD));
+        for (int l = 0; l < HDEPTH; ++l) HM_CUDA(c, dev_alloc(c, &c->w_kT[l], (size_t)8 * DM * 64));
+    }
+    {   // patch weight [1280,768] -> bf16 [1280, 1536] = [W | W]
+        HM_CUDA(c, fetch("backbone.patch_embed.proj.weight", h));
+        std::vector<float> w2((size_t)DM * KPATCH);
+        for (int n = 0; n < DM; ++n)
+            for (int k = 0; k < 768; ++k) {
+                w2[(size_t)n * KPATCH + k] = h[(size_t)n * 768 + k];
+                w2[(size_t)n * KPATCH + 768 + k] = h[(size_t)n * 768 + k];
+            }
+        float* tmp = nullptr;
+        HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&tmp), w2.size() * 4));
+        cudaError_t e1 = cudaMemcpy(tmp, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice);
+        f32_to_w16_kernel<<<(unsigned)((w2.size() + 255) / 256), 256>>>(
+            tmp, reinterpret_cast<uint16_t*>(c->w_patch2), w2.size(), (int)c->b_format);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        HM_CUDA(c, e1);
+        HM_CUDA(c, e2);
+    }
+    {   // pos table = pos[:,1:] + pos[:,:1]  (vit.py:327 adds them to x one after the other)
+        HM_CUDA(c, fetch("backbone.pos_embed", h));
+        std::vector<float> tab((size_t)TOK * DM);
+        for (int t = 0; t < TOK; ++t)
+            for (int d = 0; d < DM; ++d) tab[(size_t)t * DM + d] = h[(size_t)(t + 1) * DM + d] + h[d];
+        HM_CUDA(c, cudaMemcpy(c->pos_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    }
+    {   // layer-0 token: Linear(1,1024)(0) + pos_embedding = bias + pos  (mano_head.py:86, pose_transformer.py:350-354)
+        HM_CUDA(c, fetch("mano_head.transformer.to_token_embedding.bias", h));
+        HM_CUDA(c, fetch("mano_head.transformer.pos_embedding", h2));
+        for (int i = 0; i < HD; ++i) h[i] += h2[i];
+        HM_CUDA(c, cudaMemcpy(c->tok0, h.data(), HD * 4, cudaMemcpyHostToDevice));
+    }
+    for (int l = 0; l < HDEPTH; ++l) {   // w_kT[h][c][d] = to_kv.weight[h*64 + d][c]
+        HM_CUDA(c, fetch(dec_name(l, 1, "fn.to_kv.weight"), h));
+        std::vector<float> kt((size_t)8 * DM * 64);
+        for (int hh = 0; hh < 8; ++hh)
+            for (int cc = 0; cc < DM; ++cc)
+                for (int d = 0; d < 64; ++d)
+                    kt[((size_t)hh * DM + cc) * 64 + d] = h[(size_t)(hh * 64 + d) * DM + cc];
+        HM_CUDA(c, cudaMemcpy(c->w_kT[l], kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
+    }
+    {   // read-out: [decpose; decshape; deccam], bias + init_* (mano_head.py:93-95)
+        std::vector<float> wr((size_t)NREAD * HD), br(NREAD);
+        const char* wn[3] = {"mano_head.decpose", "mano_head.decshape", "mano_head.deccam"};
+        const char* in[3] = {"mano_head.init_hand_pose", "mano_head.init_betas", "mano_head.init_cam"};
+        const int rows[3] = {96, 10, 3};
+        int r0 = 0;
+        for (int q = 0; q < 3; ++q) {
+            HM_CUDA(c, fetch(std::string(wn[q]) + ".weight", h));
+            HM_CUDA(c, fetch(std::string(wn[q]) + ".bias", h2));
+            HM_CUDA(c, fetch(in[q], h3));
+            memcpy(&wr[(size_t)r0 * HD], h.data(), (size_t)rows[q] * HD * 4);
+            for (int r = 0; r < rows[q]; ++r) br[r0 + r] = h2[r] + h3[r];
+            r0 += rows[q];
+        }
+        HM_CUDA(c, cudaMemcpy(c->w_read, wr.data(), wr.size() * 4, cudaMemcpyHostToDevice));
+        HM_CUDA(c, cudaMemcpy(c->b_read, br.data(), br.size() * 4, cudaMemcpyHostToDevice));
+    }
+    // ---- weight tensor maps ------------------------------------------------------------------
+    const uint32_t brow = (uint32_t)(c->plan.bn / c->plan.cta_group);
+    bool ok = make_tmap_bf16_2d(&c->tm_wpatch, c->w_patch2, DM, KPATCH, KPATCH, brow);
+    for (int i = 0; i < DEPTH && ok; ++i) {
+        ok = make_tmap_bf16_2d(&c->blk[i].tm_qkv, find(c, blk_name(i, "attn.qkv.weight"))->bf16, 3 * DM, DM, DM, brow) &&
+             make_tmap_bf16_2d(&c->blk[i].tm_proj, find(c, blk_name(i, "attn.proj.weight"))->bf16, DM, DM, DM, brow) &&
+             make_tmap_bf16_2d(&c->blk[i].tm_fc1, find(c, blk_name(i, "mlp.fc1.weight"))->bf16, DFF, DM, DM, brow) &&
+             make_tmap_bf16_2d(&c->blk[i].tm_fc2, find(c, blk_name(i, "mlp.fc2.weight"))->bf16, DM, DFF, DFF, brow);
+    }
+    if (!ok) return fail(c, HM_ERR_CUDA, "weight tensor-map encoding failed");
+    // ---- cached raw pointers -----------------------------------------------------------------
+    auto F = [&](const std::string& n) { return (const float*)find(c, n)->f32; };
+    c->b_patch = F("backbone.patch_embed.proj.bias");
+    c->lnf_g = F("backbone.last_norm.weight");
+    c->lnf_b = F("backbone.last_norm.bias");
+    for (int i = 0; i < DEPTH; ++i) {
+        BlockW& w = c->blk[i];
+        w.ln1_g = F(blk_name(i, "norm1.weight")); w.ln1_b = F(blk_name(i, "norm1.bias"));
+        w.ln2_g = F(blk_name(i, "norm2.weight")); w.ln2_b = F(blk_name(i, "norm2.bias"));
+        w.b_qkv = F(blk_name(i, "attn.qkv.bias")); w.b_proj = F(blk_name(i, "attn.proj.bias"));
+        w.b_fc1 = F(blk_name(i, "mlp.fc1.bias")); w.b_fc2 = F(blk_name(i, "mlp.fc2.bias"));
+    }
+    for (int l = 0; l < HDEPTH; ++l) {
+        HeadLayerW& w = c->hl[l];
+        w.n0g = F(dec_name(l, 0, "norm.weight")); w.n0b = F(dec_name(l, 0, "norm.bias"));
+        w.n1g = F(dec_name(l, 1, "norm.weight")); w.n1b = F(dec_name(l, 1, "norm.bias"));
+        w.n2g = F(dec_name(l, 2, "norm.weight")); w.n2b = F(dec_name(l, 2, "norm.bias"));
+        w.w_sa_v = F(dec_name(l, 0, "fn.to_qkv.weight")) + (size_t)1024 * HD;
+        w.w_sa_o = F(dec_name(l, 0, "fn.to_out.0.weight")); w.b_sa_o = F(dec_name(l, 0, "fn.to_out.0.bias"));
+        w.w_q = F(dec_name(l, 1, "fn.to_q.weight"));
+        w.w_kT = c->w_kT[l];
+        w.w_v = F(dec_name(l, 1, "fn.to_kv.weight")) + (size_t)512 * DM;
+        w.w_ca_o = F(dec_name(l, 1, "fn.to_out.0.weight")); w.b_ca_o = F(dec_name(l, 1, "fn.to_out.0.bias"));
+        w.w1 = F(dec_name(l, 2, "fn.net.0.weight")); w.b1 = F(dec_name(l, 2, "fn.net.0.bias"));
+        w.w2 = F(dec_name(l, 2, "fn.net.3.weight")); w.b2 = F(dec_name(l, 2, "fn.net.3.bias"));
+    }
+    c->finalized = true;
+    return HM_OK;
+}
+
+int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, const float* posedirs,
+                const float* J_regressor, const float* lbs_weights, const int32_t* parents,
+                const int32_t* tip_ids, const int32_t* joint_map) {
+    if (!c || !v_template || !shapedirs || !posedirs || !J_regressor || !lbs_weights || !parents ||
+        !tip_ids || !joint_map)
+        return fail(c, HM_ERR_INVALID, "hm_set_mano: null argument");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    for (int j = 0; j < 16; ++j)
+        if (parents[j] >= j || parents[j] < -1) return fail(c, HM_ERR_INVALID, "hm_set_mano: parents must precede children");
+    for (int q = 0; q < 5; ++q)
+        if (tip_ids[q] < 0 || tip_ids[q] >= MANO_V) return fail(c, HM_ERR_INVALID, "hm_set_mano: tip id out of range");
+    for (int q = 0; q < 21; ++q)
+        if (joint_map[q] < 0 || joint_map[q] >= 21) return fail(c, HM_ERR_INVALID, "hm_set_mano: joint_map out of range");
+    // basis[k][coord][vertex(800)]
+    std::vector<float> basis((size_t)MANO_K * 3 * MANO_VPAD, 0.f);
+    for (int v = 0; v < MANO_V; ++v)
+        for (int cdim = 0; cdim < 3; ++cdim) {
+            basis[(size_t)(0 * 3 + cdim) * MANO_VPAD + v] = v_template[v * 3 + cdim];
+            for (int l = 0; l < 10; ++l)
+                basis[(size_t)((1 + l) * 3 + cdim) * MANO_VPAD + v] = shapedirs[(v * 3 + cdim) * 10 + l];
+            for (int k = 0; k < 135; ++k)
+                basis[(size_t)((11 + k) * 3 + cdim) * MANO_VPAD + v] = posedirs[(size_t)k * 2334 + v * 3 + cdim];
+        }
+    // folded joint regressor (double accumulation; one-time)
+    std::vector<float> jt(48), js(480);
+    for (int j = 0; j < 16; ++j)
+        for (int cdim = 0; cdim < 3; ++cdim) {
+            double a = 0;
+            for (int v = 0; v < MANO_V; ++v) a += (double)J_regressor[j * MANO_V + v] * v_template[v * 3 + cdim];
+            jt[j * 3 + cdim] = (float)a;
+            for (int l = 0; l < 10; ++l) {
+                double s = 0;
+                for (int v = 0; v < MANO_V; ++v)
+                    s += (double)J_regressor[j * MANO_V + v] * shapedirs[(v * 3 + cdim) * 10 + l];
+                js[(j * 3 + cdim) * 10 + l] = (float)s;
+            }
+        }
+    // sparse skinning weights
+    std::vector<int32_t> sidx((size_t)MANO_VPAD * MANO_MAX_NNZ, 0);
+    std::vector<float> sw((size_t)MANO_VPAD * MANO_MAX_NNZ, 0.f);
+    for (int v = 0; v < MANO_V; ++v) {
+        int n = 0;
+        for (int j = 0; j < 16; ++j) {
+            const float wv = lbs_weights[v * 16 + j];
+            if (wv != 0.f) {
+                if (n == MANO_MAX_NNZ) return fail(c, HM_ERR_INVALID, "hm_set_mano: more than 8 skinning weights on a vertex");
+                sidx[(size_t)v * MANO_MAX_NNZ + n] = j;
+                sw[(size_t)v * MANO_MAX_NNZ + n] = wv;
+                ++n;
+            }
+        }
+    }
+    for (void* p : c->mano_allocs) cudaFree(p);
+    c->mano_allocs.clear();
+    c->mano_set = false;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e != cudaSuccess) return e;
+        c->mano_allocs.push_back(d);
+        *dst = d;
+        return cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    };
+    HM_CUDA(c, up(basis.data(), basis.size() * 4, reinterpret_cast<const void**>(&c->mano.basis)));
+    HM_CUDA(c, up(jt.data(), jt.size() * 4, reinterpret_cast<const void**>(&c->mano.j_template)));
+    HM_CUDA(c, up(js.data(), js.size() * 4, reinterpret_cast<const void**>(&c->mano.j_shapedirs)));
+    HM_CUDA(c, up(sidx.data(), sidx.size() * 4, reinterpret_cast<const void**>(&c->mano.skin_idx)));
+    HM_CUDA(c, up(sw.data(), sw.size() * 4, reinterpret_cast<const void**>(&c->mano.skin_w)));
+    for (int j = 0; j < 16; ++j) c->mano.parents[j] = parents[j];
+    for (int q = 0; q < 5; ++q) c->mano.tip_ids[q] = tip_ids[q];
+    for (int q = 0; q < 21; ++q) c->mano.joint_map[q] = joint_map[q];
+    c->mano_set = true;
+    return HM_OK;
+}
+
+int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride,
+                  int frame_on_device, const double* boxes_xyxy, const uint8_t* is_right, int n,
+                  float* img_out, float* box_center, float* box_size, float* trans, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!frame_bgr || !boxes_xyxy || !is_right || !img_out || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3)
+        return fail(c, HM_ERR_INVALID, "hm_preprocess: bad arguments");
+    if (n <= 0) return fail(c, HM_ERR_INVALID, "Invalid detections format");   // infer.py:360-361
+    if (n > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_preprocess: n exceeds max_batch");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    if (c->crop_event_pending) {   // pinned staging still owned by the previous call's copy?
+        HM_CUDA(c, cudaEventSynchronize(c->crop_event));
+        c->crop_event_pending = false;
+    }
+    for (int i = 0; i < n; ++i) {
+        const double* box = boxes_xyxy + 4 * i;
+        if (!(box[2] > box[0]) || !(box[3] > box[1])) return fail(c, HM_ERR_INVALID, "hm_preprocess: empty box");
+        double cx, cy, size, M[6];
+        box_to_affine(box, &cx, &cy, &size, M);
+        invert_affine(M, c->crop_host[i].m);
+        c->crop_host[i].flip = is_right[i] ? 0 : 1;
+        c->crop_host[i].pad = 0;
+        if (box_center) { box_center[2 * i] = (float)cx; box_center[2 * i + 1] = (float)cy; }
+        if (box_size) box_size[i] = (float)size;
+        if (trans) for (int q = 0; q < 6; ++q) trans[6 * i + q] = (float)M[q];
+    }
+    const uint8_t* frame = frame_bgr;
+    if (!frame_on_device) {
+        const size_t bytes = (size_t)H * (size_t)row_stride;
+        if (!c->frame_dev || bytes > (size_t)c->cfg.max_frame_bytes)
+            return fail(c, HM_ERR_INVALID, "hm_preprocess: frame larger than hm_config.max_frame_bytes");
+        HM_CUDA(c, cudaMemcpyAsync(c->frame_dev, frame_bgr, bytes, cudaMemcpyHostToDevice, s));
+        frame = c->frame_dev;
+    }
+    HM_CUDA(c, cudaMemcpyAsync(c->crop_dev, c->crop_host, (size_t)n * sizeof(CropParams), cudaMemcpyHostToDevice, s));
+    HM_CUDA(c, cudaEventRecord(c->crop_event, s));
+    c->crop_event_pending = true;
+    crop_warp_normalize_kernel<<<dim3(256, n), 256, 0, s>>>(frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
+int hm_backbone(hm_ctx* c, const float* img, int B, float* feats, void* stream) {
+    int rc = check_ready(c, B, true, false);
+    if (rc) return rc;
+    if (!img || !feats) return fail(c, HM_ERR_INVALID, "hm_backbone: null pointer");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    return backbone_impl(c, img, B, feats, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hm_mano_head(hm_ctx* c, const float* feats, int B, const hm_outputs* out, void* stream) {
+    int rc = check_ready(c, B, true, false);
+    if (rc) return rc;
+    if (!feats || !out) return fail(c, HM_ERR_INVALID, "hm_mano_head: null pointer");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    return head_impl(c, feats, B, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hm_mano_lbs(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
+                float* verts, float* joints21, float* kp2d, void* stream) {
+    int rc = check_ready(c, B, false, true);
+    if (rc) return rc;
+    if (!betas || !rotmats || !verts || !joints21) return fail(c, HM_ERR_INVALID, "hm_mano_lbs: null pointer");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    return lbs_impl(c, betas, rotmats, cam_t, B, verts, joints21, kp2d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hm_forward(hm_ctx* c, const float* img, int B, const hm_outputs* out, void* stream) {
+    int rc = check_ready(c, B, true, true);
+    if (rc) return rc;
+    if (!img || !out) return fail(c, HM_ERR_INVALID, "hm_forward: null pointer");
+    if (!out->pred_vertices || !out->pred_keypoints_3d || !out->pred_keypoints_2d)
+        return fail(c, HM_ERR_INVALID, "hm_forward: pred_vertices / pred_keypoints_3d / pred_keypoints_2d are required");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    float* feats = out->conditioning_feats ? out->conditioning_feats : c->feats;
+    if ((rc = backbone_impl(c, img, B, feats, s))) return rc;
+    if ((rc = head_impl(c, feats, B, out, s))) return rc;
+    return lbs_impl(c, c->hbetas, c->hrot, c->hcamt, B, out->pred_vertices, out->pred_keypoints_3d,
+                    out->pred_keypoints_2d, s);
+}
+
+int hm_forward_launch_count(const hm_ctx*) {
+    // im2col + patch GEMM + 32 x (LN, qkv, attention, proj, LN, fc1, fc2) + last LN
+    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO
+    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + 1;
+}
+
+// ---- test hooks ---------------------------------------------------------------------------------
+int hm_test_gemm(hm_ctx* c, int cta_group, int bn, int epi, int w_format, const uint16_t* A,
+                 const uint16_t* W, const float* bias, const float* pos, void* out, int M, int N,
+                 int K, void* stream) {
+    if (!c || !A || !W || !bias || !out) return fail(c, HM_ERR_INVALID, "hm_test_gemm: null pointer");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    CUtensorMap ta, tb;
+    if (!make_tmap_bf16_2d(&ta, A, M, K, K, GEMM_BM) || !make_tmap_bf16_2d(&tb, W, N, K, K, bn / (cta_group == 1 ? 1 : 2)))
+        return fail(c, HM_ERR_CUDA, "hm_test_gemm: tensor map encoding failed");
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
+    p.b_format = w_format ? 1u : 0u;
+    GemmPlan plan{cta_group == 1 ? 1 : 2, bn};
+    HM_CUDA(c, gemm_launch(plan, epi, ta, tb, p, c->num_sms, reinterpret_cast<cudaStream_t>(stream)));
+    return HM_OK;
+}
+
+int hm_test_layernorm(hm_ctx* c, const float* x, const float* gamma, const float* beta, void* y,
+                      int rows, float eps, int out_bf16, void* stream) {
+    if (!c || !x || !gamma || !beta || !y) return fail(c, HM_ERR_INVALID, "hm_test_layernorm: null pointer");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (out_bf16) launch_ln<10, __half>(x, gamma, beta, reinterpret_cast<__half*>(y), rows, eps, s);
+    else launch_ln<10, float>(x, gamma, beta, reinterpret_cast<float*>(y), rows, eps, s);
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
+int hm_test_attention(hm_ctx* c, const uint16_t* qkv, uint16_t* out, int B, void* stream) {
+    if (!c || !qkv || !out || B <= 0) return fail(c, HM_ERR_INVALID, "hm_test_attention: bad arguments");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out),
+        0.11180339887498948f * 1.4426950408889634f);
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
+}  // extern "C"

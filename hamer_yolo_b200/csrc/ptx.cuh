@@ -240,11 +240,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor, kind::f16: A,B = bf16 K-major, D = f32, shape M x N x 16.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
+// Instruction descriptor, kind::f16: A, B K-major, D = f32, shape M x N x 16.
+// a_fmt / b_fmt: 0 = f16, 1 = bf16 (independent fields: the activations are fp16, the weights bf16).
+__host__ __device__ constexpr uint32_t make_idesc_f16kind_f32(int a_fmt, int b_fmt, int M, int N) {
     return (1u << 4)                       // D format f32
-           | (1u << 7)                     // A format bf16
-           | (1u << 10)                    // B format bf16
+           | (static_cast<uint32_t>(a_fmt) << 7)
+           | (static_cast<uint32_t>(b_fmt) << 10)
            | (static_cast<uint32_t>(N >> 3) << 17)
            | (static_cast<uint32_t>(M >> 4) << 24);
 }

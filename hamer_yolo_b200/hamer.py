@@ -1,0 +1,273 @@
+"""Drop-in mirror of the reference's model API, backed by libhamer_b200.so.
+
+Reference interfaces mirrored (names, argument meaning, returned dict layout, error behaviour):
+  hamer/hamer/models/hamer.py:19-72    HAMER.__init__        -> HAMER(cfg, ...)
+  hamer/hamer/models/hamer.py:99-156   HAMER.forward_step    -> HAMER.forward_step / forward
+  hamer/hamer/models/hamer.py:269-277  HAMER.forward(batch)  -> (output, pred_mano_params)
+  hamer/hamer/models/__init__.py:32-47 load_hamer(ckpt)      -> load_hamer(ckpt, ...)
+PyTorch is used only to own device memory and hand pointers + the current stream to the C ABI.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .configs import default_config
+from .mano_data import load_mano_pkl, synthetic_mano
+
+IMG = 256
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class _ManoHandle:
+    """What callers read from ``model.mano`` (infer.py:148-152 uses ``.faces``)."""
+
+    def __init__(self, data):
+        self.data = data
+        self.faces = data['faces']
+
+
+class Engine:
+    """Owns one hm_ctx (one device, one stream user).  Thin: argument marshalling only."""
+
+    def __init__(self, device, max_batch=64, max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('hamer_b200 runs on a CUDA (sm_100a) device only; there is no CPU path')
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device('cuda', self.index)
+        self.max_batch = int(max_batch)
+        self.max_frame_bytes = int(max_frame_bytes)
+        cfg = _lib.HmConfig(max_batch=self.max_batch, max_frame_bytes=self.max_frame_bytes,
+                            gemm_cta_group=int(gemm_cta_group))
+        h = C.c_void_p()
+        rc = self.lib.hm_create(C.byref(h), self.index, C.byref(cfg))
+        if rc != 0:
+            raise _lib.HmError(rc, self.lib.hm_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.hm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def check(self, rc):
+        return _lib.check(self.h, rc)
+
+    # -- weights / MANO --------------------------------------------------------------------------
+    def set_weight(self, name, tensor):
+        t = tensor.detach().to('cpu', torch.float32).contiguous()
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        self.check(self.lib.hm_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+
+    def finalize_weights(self):
+        self.check(self.lib.hm_finalize_weights(self.h))
+
+    def set_mano(self, m):
+        arr = lambda k, dt: np.ascontiguousarray(m[k], dtype=dt)
+        keep = [arr('v_template', np.float32), arr('shapedirs', np.float32), arr('posedirs', np.float32),
+                arr('J_regressor', np.float32), arr('lbs_weights', np.float32), arr('parents', np.int32),
+                arr('tip_ids', np.int32), arr('joint_map', np.int32)]
+        assert keep[0].shape == (778, 3) and keep[1].shape == (778, 3, 10) and keep[2].shape == (135, 2334)
+        assert keep[3].shape == (16, 778) and keep[4].shape == (778, 16)
+        self.check(self.lib.hm_set_mano(self.h, *[C.c_void_p(a.ctypes.data) for a in keep]))
+
+    # -- stages ----------------------------------------------------------------------------------
+    def _outputs(self, B, want_feats=False):
+        dev = self.device
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        t = {'pred_cam': f(B, 3), 'global_orient': f(B, 1, 3, 3), 'hand_pose': f(B, 15, 3, 3),
+             'betas': f(B, 10), 'pred_cam_t': f(B, 3), 'focal_length': f(B, 2),
+             'pred_keypoints_3d': f(B, 21, 3), 'pred_vertices': f(B, 778, 3),
+             'pred_keypoints_2d': f(B, 21, 2)}
+        if want_feats:
+            t['conditioning_feats'] = f(B, 192, 1280)
+        return t
+
+    @staticmethod
+    def _struct(t, lo, hi):
+        s = _lib.HmOutputs()
+        for name, _ in _lib.HmOutputs._fields_:
+            setattr(s, name, t[name][lo:hi].data_ptr() if name in t else None)
+        return s
+
+    def forward(self, img, want_feats=False):
+        """img: CUDA float32 [B,3,256,256].  Returns dict of CUDA tensors (hm_outputs fields)."""
+        B = img.shape[0]
+        t = self._outputs(B, want_feats)
+        with torch.cuda.device(self.device):
+            for lo in range(0, B, self.max_batch):          # transparently chunk large batches
+                hi = min(B, lo + self.max_batch)
+                s = self._struct(t, lo, hi)
+                self.check(self.lib.hm_forward(self.h, _ptr(img[lo:hi]), hi - lo, C.byref(s), self.stream()))
+        return t
+
+    def backbone(self, img):
+        B = img.shape[0]
+        feats = torch.empty(B, 192, 1280, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            for lo in range(0, B, self.max_batch):
+                hi = min(B, lo + self.max_batch)
+                self.check(self.lib.hm_backbone(self.h, _ptr(img[lo:hi]), hi - lo, _ptr(feats[lo:hi]), self.stream()))
+        return feats
+
+    def mano_head(self, feats):
+        B = feats.shape[0]
+        t = self._outputs(B)
+        with torch.cuda.device(self.device):
+            for lo in range(0, B, self.max_batch):
+                hi = min(B, lo + self.max_batch)
+                s = self._struct(t, lo, hi)
+                self.check(self.lib.hm_mano_head(self.h, _ptr(feats[lo:hi]), hi - lo, C.byref(s), self.stream()))
+        return t
+
+    def mano_lbs(self, betas, rotmats, cam_t=None):
+        """betas [B,10], rotmats [B,16,3,3] (CUDA f32) -> vertices [B,778,3], joints [B,21,3]
+        (+ crop-normalised 2D keypoints [B,21,2] when cam_t [B,3] is given)."""
+        B = betas.shape[0]
+        verts = torch.empty(B, 778, 3, device=self.device, dtype=torch.float32)
+        joints = torch.empty(B, 21, 3, device=self.device, dtype=torch.float32)
+        kp2d = torch.empty(B, 21, 2, device=self.device, dtype=torch.float32) if cam_t is not None else None
+        with torch.cuda.device(self.device):
+            self.check(self.lib.hm_mano_lbs(self.h, _ptr(betas), _ptr(rotmats), _ptr(cam_t), B,
+                                            _ptr(verts), _ptr(joints), _ptr(kp2d), self.stream()))
+        return (verts, joints, kp2d) if cam_t is not None else (verts, joints)
+
+    def preprocess(self, frame_bgr, boxes_xyxy, is_right, out=None):
+        """frame_bgr: HxWx3 uint8 numpy (host) or CUDA uint8 tensor.  Returns
+        (img [n,3,256,256] CUDA f32, box_center [n,2], box_size [n], trans [n,2,3]) (numpy f32)."""
+        boxes = np.ascontiguousarray(boxes_xyxy, dtype=np.float64).reshape(-1, 4)
+        n = boxes.shape[0]
+        right = np.ascontiguousarray(is_right, dtype=np.uint8).reshape(-1)
+        img = out if out is not None else torch.empty(n, 3, IMG, IMG, device=self.device, dtype=torch.float32)
+        center = np.empty((n, 2), np.float32)
+        size = np.empty((n,), np.float32)
+        trans = np.empty((n, 2, 3), np.float32)
+        if isinstance(frame_bgr, torch.Tensor):
+            assert frame_bgr.is_cuda and frame_bgr.dtype == torch.uint8 and frame_bgr.stride(-1) == 1
+            H, W = frame_bgr.shape[:2]
+            fptr, stride, on_dev, keep = frame_bgr.data_ptr(), frame_bgr.stride(0), 1, frame_bgr
+        else:
+            keep = np.ascontiguousarray(frame_bgr)
+            assert keep.dtype == np.uint8 and keep.ndim == 3 and keep.shape[2] == 3
+            H, W = keep.shape[:2]
+            fptr, stride, on_dev = keep.ctypes.data, keep.strides[0], 0
+        with torch.cuda.device(self.device):
+            self.check(self.lib.hm_preprocess(
+                self.h, C.c_void_p(fptr), H, W, stride, on_dev, C.c_void_p(boxes.ctypes.data),
+                C.c_void_p(right.ctypes.data), n, _ptr(img), C.c_void_p(center.ctypes.data),
+                C.c_void_p(size.ctypes.data), C.c_void_p(trans.ctypes.data), self.stream()))
+        return img, center, size, trans
+
+    def launch_count(self):
+        return int(self.lib.hm_forward_launch_count(self.h))
+
+
+class HAMER:
+    """The reference's ``HAMER`` (inference surface).  ``model(batch)`` returns the same two
+    dicts as hamer.py:124-156; tensors live on the model's CUDA device, float32."""
+
+    def __init__(self, cfg=None, init_renderer=False, mano=None, device='cuda:0', max_batch=64,
+                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0):
+        self.cfg = cfg if cfg is not None else default_config()
+        if self.cfg.MODEL.IMAGE_SIZE != 256:
+            raise AssertionError(f'MODEL.IMAGE_SIZE ({self.cfg.MODEL.IMAGE_SIZE}) should be 256 for ViT backbone')
+        self.engine = Engine(device, max_batch, max_frame_bytes, gemm_cta_group)
+        self.device = self.engine.device
+        self.training = False
+        if mano is None:
+            mano = self._load_mano_from_cfg()
+        self.mano = _ManoHandle(mano)
+        self.engine.set_mano(mano)
+        self._have_weights = False
+
+    def _load_mano_from_cfg(self):
+        path = os.path.join(str(self.cfg.MANO.MODEL_PATH), 'MANO_RIGHT.pkl')
+        if not os.path.exists(path):
+            raise FileNotFoundError(f'MANO model not found at {path} (cfg.MANO.MODEL_PATH); pass mano=... explicitly')
+        return load_mano_pkl(path)
+
+    # -- nn.Module-like surface the reference's callers use --------------------------------------
+    def to(self, device):
+        d = torch.device(device)
+        if d.type != 'cuda':
+            raise RuntimeError('hamer_b200.HAMER has no CPU path')
+        idx = d.index if d.index is not None else torch.cuda.current_device()
+        if idx != self.engine.index:
+            raise RuntimeError(f'model is bound to cuda:{self.engine.index}; build it with device=cuda:{idx}')
+        return self
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, state_dict, strict=False):
+        """Accepts the reference checkpoint's key layout; other keys (e.g. the
+        discriminator, 'mano.*' buffers) are ignored like load_from_checkpoint(strict=False)."""
+        used = 0
+        for k, v in state_dict.items():
+            if k.startswith('backbone.') or k.startswith('mano_head.'):
+                self.engine.set_weight(k, v)
+                used += 1
+        self.engine.finalize_weights()
+        self._have_weights = True
+        return used
+
+    def forward_step(self, batch, train=False):
+        if train:
+            raise NotImplementedError('inference only')
+        x = batch['img']
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, IMG, IMG):
+            raise ValueError(f"batch['img'] must be [B,3,256,256], got {tuple(x.shape)}")
+        x = x.to(self.device, torch.float32).contiguous()
+        B = x.shape[0]
+        t = self.engine.forward(x, want_feats=False)
+        pred_mano_params = {'global_orient': t['global_orient'], 'hand_pose': t['hand_pose'], 'betas': t['betas']}
+        output = {
+            'pred_cam': t['pred_cam'],
+            'pred_mano_params': {k: v.clone() for k, v in pred_mano_params.items()},   # hamer.py:126
+            'pred_cam_t': t['pred_cam_t'],
+            'focal_length': t['focal_length'],
+            'pred_keypoints_3d': t['pred_keypoints_3d'].reshape(B, -1, 3),
+            'pred_vertices': t['pred_vertices'].reshape(B, -1, 3),
+            'pred_keypoints_2d': t['pred_keypoints_2d'].reshape(B, -1, 2),
+        }
+        pred_mano_params['trans'] = t['pred_cam_t']                                     # hamer.py:155
+        return output, pred_mano_params
+
+    def forward(self, batch):
+        return self.forward_step(batch, train=False)
+
+    __call__ = forward
+
+
+def load_hamer(checkpoint_path=None, mano=None, device='cuda:0', max_batch=64, cfg=None, state_dict=None):
+    """load_hamer (models/__init__.py:32-47): returns (model, model_cfg).  ``checkpoint_path`` is a
+    Lightning checkpoint ({'state_dict': ...}) or a plain state dict saved with torch.save;
+    ``state_dict`` can be passed directly instead."""
+    cfg = cfg if cfg is not None else default_config()
+    if cfg.MODEL.BACKBONE.TYPE == 'vit' and 'BBOX_SHAPE' not in cfg.MODEL:
+        assert cfg.MODEL.IMAGE_SIZE == 256
+        cfg.MODEL.BBOX_SHAPE = [192, 256]
+    model = HAMER(cfg, mano=mano, device=device, max_batch=max_batch)
+    if state_dict is None:
+        if checkpoint_path is None:
+            raise ValueError('load_hamer needs checkpoint_path or state_dict')
+        ckpt = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
+        state_dict = ckpt.get('state_dict', ckpt)
+    model.load_state_dict(state_dict, strict=False)
+    return model, cfg

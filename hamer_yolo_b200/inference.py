@@ -1,0 +1,185 @@
+"""Drop-in mirror of the reference's pipeline wrapper ``hamer_inference`` (hamer/infer.py:117-528)
+and of the per-image ``.npy`` writer (hamer/infer.py:1082-1096, 1223-1318).
+
+  hamer_inference.__init__            infer.py:118-146
+  hamer_inference.prepare_batch_bbox  infer.py:154-259   -> hm_preprocess (crop_warp.cuh)
+  hamer_inference.estimate_from_rgb   infer.py:354-528   -> hm_forward + camera post-processing
+  matrix_to_axis_angle                infer.py:1082-1096 (cv2.Rodrigues, host, kept for exactness)
+  process_batch_manopara (npy layout) infer.py:1296-1312 -> hand_record / save_image_results
+"""
+import os
+
+import numpy as np
+import torch
+
+from .hamer import HAMER, load_hamer
+
+
+def perspective_projection(points, translation, focal_length):
+    """hamer/hamer/utils/geometry.py:72-109 with identity rotation and zero camera centre."""
+    p = points + translation.unsqueeze(1)
+    p = p / p[:, :, -1].unsqueeze(-1)
+    return p[:, :, :2] * focal_length.unsqueeze(1)
+
+
+def custom_cam_crop_to_full(cam_bbox, box_center, box_size, img_size, fx, fy, cx, cy):
+    """hamer/hamer/utils/renderer.py:24-74 (depth_refine=None)."""
+    b = cam_bbox.shape[0]
+    dev = cam_bbox.device
+
+    def vec(v):
+        v = torch.as_tensor(v, dtype=torch.float32, device=dev)
+        return v.reshape(-1).expand(b) if v.numel() == 1 else v.reshape(b)
+
+    fx, fy, cx, cy = vec(fx), vec(fy), vec(cx), vec(cy)
+    bs = box_size * cam_bbox[:, 0] + 1e-9
+    tz = 2 * fx / bs
+    tx = (2 * (box_center[:, 0] - cx) / bs) + cam_bbox[:, 1]
+    ty = (2 * (box_center[:, 1] - cy) / bs) + cam_bbox[:, 2]
+    if not torch.allclose(fx, fy):
+        ty = ty * (fx / fy)
+    return torch.stack([tx, ty, tz], dim=-1)
+
+
+class hamer_inference:
+    """Same constructor contract as the reference: ``cfg`` carries ``ckpt_path`` (and optionally
+    ``mano_path``); alternatively pass an already built ``model``."""
+
+    def __init__(self, cfg=None, model=None, device='cuda:0', max_batch=64, mano=None):
+        if model is None:
+            if getattr(cfg, 'use_onnx', False):
+                raise NotImplementedError('the ONNX backend is out of scope (no multi-backend dispatch)')
+            model, model_cfg = load_hamer(cfg.ckpt_path, mano=mano, device=device, max_batch=max_batch)
+        else:
+            model_cfg = model.cfg
+        self.use_onnx = False
+        self.model = model.eval()
+        self.device = model.device
+        self.cfg = model_cfg
+        self.mean = 255. * np.array(self.cfg.MODEL.IMAGE_MEAN)
+        self.std = 255. * np.array(self.cfg.MODEL.IMAGE_STD)
+
+    # -- crop / warp / normalise -----------------------------------------------------------------
+    def prepare_batch_bbox(self, img_0, bboxs):
+        """infer.py:154-259.  Returns the same dict; 'img' is already on the device (the
+        reference moves it there in estimate_from_rgb, infer.py:366-368)."""
+        boxes, right = [], []
+        for bbox in bboxs:
+            if isinstance(bbox, (list, tuple)) and len(bbox) == 2:
+                hand_cls, coords = bbox[0], bbox[1]
+                if not (isinstance(coords, (list, tuple, np.ndarray)) and len(coords) == 4):
+                    raise ValueError(f'Invalid coordinates format: Expected [x1,y1,x2,y2], got {coords}')
+            else:
+                raise ValueError(f'Invalid bbox format: Expected [class, coords], got {bbox}')
+            boxes.append([float(v) for v in coords])
+            right.append(1 if hand_cls == 'right' else 0)
+        eng = self.model.engine
+        n = len(boxes)
+        imgs, centers, sizes, trans = [], [], [], []
+        for lo in range(0, n, eng.max_batch):
+            hi = min(n, lo + eng.max_batch)
+            i, c, s, t = eng.preprocess(img_0, boxes[lo:hi], right[lo:hi])
+            imgs.append(i); centers.append(c); sizes.append(s); trans.append(t)
+        dev = self.device
+        H, W = img_0.shape[:2]
+        trans = torch.from_numpy(np.concatenate(trans)).to(dev)
+        return {
+            'img': torch.cat(imgs) if len(imgs) > 1 else imgs[0],
+            'box_center': torch.from_numpy(np.concatenate(centers)).to(dev),
+            'box_size': torch.from_numpy(np.concatenate(sizes)).to(dev),
+            'img_size': torch.tensor([[W, H]] * n, dtype=torch.float32, device=dev),
+            'inv_trans': trans,            # the reference returns the forward transform twice
+            'trans': trans.clone(),
+            'do_flip': torch.tensor([0.0 if r else 1.0 for r in right], dtype=torch.float32, device=dev),
+        }
+
+    # -- full per-image estimate -----------------------------------------------------------------
+    @torch.no_grad()
+    def estimate_from_rgb(self, img_0, detections, k_real=None):
+        if not isinstance(detections, list) or len(detections) == 0:
+            raise ValueError('Invalid detections format')                     # infer.py:360-361
+        batch = self.prepare_batch_bbox(img_0, detections)
+        out, params = self.model(batch)
+        pred_cam = out['pred_cam']
+        box_center, box_size = batch['box_center'], batch['box_size']
+        img_size, do_flip = batch['img_size'], batch['do_flip']
+        kp3d = out['pred_keypoints_3d']
+        kp3d[:, :, 0] = kp3d[:, :, 0] * do_flip.unsqueeze(1)                  # infer.py:392 (in place)
+        cam = pred_cam.clone()
+        cam[:, 1] = cam[:, 1] * (1.0 - 2.0 * do_flip.view(-1))               # infer.py:402-409
+        if k_real is not None:
+            k = torch.as_tensor(np.asarray(k_real) if not torch.is_tensor(k_real) else k_real,
+                                dtype=torch.float32, device=self.device)
+            if k.dim() == 2:
+                fx, fy, cx, cy = k[0, 0], k[1, 1], k[0, 2], k[1, 2]
+            else:
+                fx, fy, cx, cy = k[:, 0, 0], k[:, 1, 1], k[:, 0, 2], k[:, 1, 2]
+            cam_t_full = custom_cam_crop_to_full(cam, box_center, box_size, img_size, fx, fy, cx, cy)
+            scaled_focal_length = fx.unsqueeze(0) if fx.dim() == 0 else fx
+            kp_cam = kp3d + cam_t_full.unsqueeze(1)
+            depth = kp_cam[:, :, 2:3] + 1e-9
+            u = kp_cam[:, :, 0:1] / depth * fx.reshape(-1, 1, 1) + cx.reshape(-1, 1, 1)
+            v = kp_cam[:, :, 1:2] / depth * fy.reshape(-1, 1, 1) + cy.reshape(-1, 1, 1)
+            kp2d = torch.cat([u, v], dim=-1)
+        else:
+            scaled_focal_length = (self.cfg.EXTRA.FOCAL_LENGTH / self.cfg.MODEL.IMAGE_SIZE *
+                                   img_size.max(dim=1)[0])
+            cam_t_full = custom_cam_crop_to_full(cam, box_center, box_size, img_size,
+                                                 scaled_focal_length, scaled_focal_length,
+                                                 img_size[:, 0] / 2.0, img_size[:, 1] / 2.0)
+            kp2d = perspective_projection(kp3d, cam_t_full,
+                                          torch.stack([scaled_focal_length, scaled_focal_length], dim=1))
+        out['pred_keypoints_2d_full'] = kp2d
+        out['pred_cam_t_full'] = cam_t_full
+        out['img'] = batch['img']
+        out['focal_length'] = scaled_focal_length
+        out['trans'] = batch['trans']
+        out['do_flip'] = do_flip
+        out['inv_trans'] = batch['inv_trans']
+        return out, params
+
+
+# -- npy output layout (infer.py:1082-1096, 1279-1312) --------------------------------------------
+def matrix_to_axis_angle(rot_mats):
+    import cv2
+    if isinstance(rot_mats, np.ndarray) and rot_mats.ndim == 2:
+        rot_mats = [rot_mats]
+    return np.concatenate([cv2.Rodrigues(np.asarray(m))[0].flatten() for m in rot_mats])
+
+
+def hand_record(output, index, is_right):
+    """One hand's dict exactly as process_batch_manopara stores it (infer.py:1279-1303)."""
+    import cv2
+    mp = output['pred_mano_params']
+    betas = mp['betas'][index].detach().cpu().numpy().squeeze()
+    hand_pose_aa = matrix_to_axis_angle(mp['hand_pose'][index].detach().cpu().numpy())
+    go = mp['global_orient'][index].detach().cpu().numpy().squeeze()
+    if go.ndim == 3:
+        go = go[0]
+    global_aa = cv2.Rodrigues(go)[0].flatten()
+    cam_t = output['pred_cam_t_full'][index].detach().cpu().numpy().squeeze()
+    return {'betas': betas, 'theta': np.concatenate((global_aa, hand_pose_aa)),
+            'pose_hand': hand_pose_aa, 'pose_global': global_aa, 'cam_t': cam_t, 'is_right': is_right}
+
+
+def process_image(hamer, image, detection_list, k_real=None):
+    """Inner loop of process_batch_manopara (infer.py:1268-1308) for one image, batched over the
+    hands instead of one model call per hand.  Returns {'left': d|None, 'right': d|None}; a later
+    hand with the same label overwrites an earlier one, as in the reference."""
+    results = {'left': None, 'right': None}
+    if not detection_list:
+        return results
+    output, _ = hamer.estimate_from_rgb(image, list(detection_list), k_real)
+    for i, bbox in enumerate(detection_list):
+        label = bbox[0]
+        results[label] = hand_record(output, i, label == 'right')
+    return results
+
+
+def save_image_results(output_folder, file_name, image_results):
+    """np.save(f"{stem}.npy", {'left':..., 'right':...}) (infer.py:1310-1312); read back with
+    np.load(..., allow_pickle=True).item() (infer.py:1350)."""
+    os.makedirs(output_folder, exist_ok=True)
+    path = os.path.join(output_folder, f'{file_name}.npy')
+    np.save(path, image_results)
+    return path

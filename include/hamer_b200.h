@@ -1,0 +1,141 @@
+/*
+ * hamer_b200 - C ABI of the B200-native HaMeR hot path (libhamer_b200.so).
+ *
+ * This is the drop-in boundary: every entry point replaces a Python/PyTorch interface of the
+ * reference (2646207530/hamer-yolo, paths below are relative to its root).  The reference is pure
+ * Python, so its "FFI" for this path is a ctypes binding; signatures use plain
+ * pointers and sizes only - no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative hm_status on failure; the message is
+ *     available from hm_last_error(ctx).  No C++ exception crosses the ABI.
+ *   - the caller owns every tensor; the library owns only packed weights, MANO tables and a
+ *     workspace sized at hm_create() for max_batch crops.
+ *   - all device work is enqueued on the cudaStream_t passed as `stream` (a void*; 0 = default
+ *     stream) without host synchronisation unless stated; hm_forward() performs no allocation and
+ *     is CUDA-graph capturable.
+ *   - a context is bound to one device and is not thread-safe (one context per rank / stream).
+ *   - "device" pointers must be valid on the context's device; "host" pointers are ordinary memory.
+ */
+#ifndef HAMER_B200_H
+#define HAMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hm_ctx hm_ctx;
+
+typedef enum hm_status {
+    HM_OK = 0,
+    HM_ERR_INVALID = -1,      /* bad argument / shape / missing weight */
+    HM_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed */
+    HM_ERR_STATE = -3,        /* weights or MANO tables not set */
+    HM_ERR_UNSUPPORTED = -4   /* not an sm_100 device */
+} hm_status;
+
+typedef struct hm_config {
+    int32_t max_batch;        /* largest B of hm_forward / n of hm_preprocess */
+    int32_t max_frame_bytes;  /* largest H*row_stride accepted by hm_preprocess (host frames) */
+    int32_t gemm_cta_group;   /* 0 = default (2: CTA-pair UMMA M=256), 1 = single-CTA tiles */
+    int32_t weights_f16;      /* 0 = backbone weights as bf16 operands (default), 1 = as fp16 */
+    int32_t reserved[4];
+} hm_config;
+
+/* Device pointers of the tensors HAMER.forward_step returns (hamer/hamer/models/hamer.py:124-156).
+ * All float32, contiguous, leading dimension B.  Any pointer may be NULL to skip that output,
+ * except that pred_vertices / pred_keypoints_3d / pred_keypoints_2d need nothing else. */
+typedef struct hm_outputs {
+    float* pred_cam;           /* [B,3]        output['pred_cam'] */
+    float* global_orient;      /* [B,1,3,3]    pred_mano_params['global_orient'] */
+    float* hand_pose;          /* [B,15,3,3]   pred_mano_params['hand_pose'] */
+    float* betas;              /* [B,10]       pred_mano_params['betas'] */
+    float* pred_cam_t;         /* [B,3]        output['pred_cam_t'] (= params['trans']) */
+    float* focal_length;       /* [B,2]        output['focal_length'] (5000) */
+    float* pred_keypoints_3d;  /* [B,21,3] */
+    float* pred_vertices;      /* [B,778,3] */
+    float* pred_keypoints_2d;  /* [B,21,2] */
+    float* conditioning_feats; /* [B,192,1280] backbone output, optional (NULL to skip) */
+} hm_outputs;
+
+/* ---- life cycle ------------------------------------------------------------------------------
+ * replaces load_hamer() / HAMER.__init__ (hamer/hamer/models/__init__.py:32-47, models/hamer.py:21-72) */
+int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg);
+void hm_destroy(hm_ctx* ctx);
+const char* hm_last_error(const hm_ctx* ctx);   /* ctx may be NULL: last hm_create error */
+
+/* ---- weights ---------------------------------------------------------------------------------
+ * One call per state-dict entry of the reference checkpoint (key layout: SURVEY.md section 5;
+ * e.g. "backbone.blocks.0.attn.qkv.weight", "mano_head.transformer.transformer.layers.0.1.fn.to_kv.weight",
+ * "mano_head.init_hand_pose").  `data` is a HOST pointer to float32 values in the reference's own
+ * layout; matrices used by the backbone GEMMs are converted to bf16 once (they must be
+ * bf16-representable for the 0.5 mm parity bar).  Replaces
+ * HAMER.load_from_checkpoint(..., strict=False) (models/__init__.py:46). */
+int hm_set_weight(hm_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Checks that every tensor is present and builds the fused tables (positional table, decoder
+ * constants).  Must be called once after the last hm_set_weight. */
+int hm_finalize_weights(hm_ctx* ctx);
+
+/* MANO model data in the layout smplx.MANOLayer builds (HOST pointers, float32 / int32):
+ * v_template[778,3] shapedirs[778,3,10] posedirs[135,2334] J_regressor[16,778] lbs_weights[778,16]
+ * parents[16] (root -1) tip_ids[5] joint_map[21].  Replaces MANO.__init__
+ * (hamer/hamer/models/mano_wrapper.py:12-30). */
+int hm_set_mano(hm_ctx* ctx, const float* v_template, const float* shapedirs, const float* posedirs,
+                const float* J_regressor, const float* lbs_weights, const int32_t* parents,
+                const int32_t* tip_ids, const int32_t* joint_map);
+
+/* ---- the hot path ----------------------------------------------------------------------------
+ * hm_preprocess replaces hamer_inference.prepare_batch_bbox (hamer/infer.py:154-259):
+ *   frame_bgr : H x W x 3 uint8, BGR, `row_stride` bytes per row; host memory unless
+ *               frame_on_device != 0
+ *   boxes_xyxy: HOST [n,4] float64 (x1,y1,x2,y2), is_right: HOST [n] (1 = 'right', 0 = flip)
+ *   img_out   : DEVICE [n,3,256,256] float32, normalised RGB        (batch['img'])
+ *   box_center: HOST [n,2] f32, box_size: HOST [n] f32, trans: HOST [n,2,3] f32 (batch['trans'],
+ *               also returned by the reference as 'inv_trans'); any of the three may be NULL.
+ * Synchronises `stream` only if it has to recycle its pinned staging buffer. */
+int hm_preprocess(hm_ctx* ctx, const uint8_t* frame_bgr, int H, int W, int64_t row_stride,
+                  int frame_on_device, const double* boxes_xyxy, const uint8_t* is_right, int n,
+                  float* img_out, float* box_center, float* box_size, float* trans, void* stream);
+
+/* hm_forward replaces HAMER.forward(batch) (hamer/hamer/models/hamer.py:269-277 -> forward_step
+ * :99-156): img = batch['img'], DEVICE [B,3,256,256] float32. */
+int hm_forward(hm_ctx* ctx, const float* img, int B, const hm_outputs* out, void* stream);
+
+/* Stages of hm_forward, individually callable (same kernels):
+ *   hm_backbone  = self.backbone(x[:,:,:,32:-32])          (hamer.py:119; backbones/vit.py:320-339)
+ *   hm_mano_head = self.mano_head(feats) + pred_cam_t      (hamer.py:121-134; heads/mano_head.py:61-115)
+ *   hm_mano_lbs  = self.mano(...) + perspective_projection (hamer.py:143-152; mano_wrapper.py:32-44)
+ * hm_mano_lbs: betas DEVICE [B,10], rotmats DEVICE [B,16,3,3] (global_orient then hand_pose),
+ * cam_t DEVICE [B,3] or NULL, verts DEVICE [B,778,3], joints21 DEVICE [B,21,3], kp2d DEVICE
+ * [B,21,2] or NULL.  B is not limited by max_batch. */
+int hm_backbone(hm_ctx* ctx, const float* img, int B, float* feats, void* stream);
+int hm_mano_head(hm_ctx* ctx, const float* feats, int B, const hm_outputs* out, void* stream);
+int hm_mano_lbs(hm_ctx* ctx, const float* betas, const float* rotmats, const float* cam_t, int B,
+                float* verts, float* joints21, float* kp2d, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------------*/
+/* Number of kernels hm_forward(B) launches (for bench.py's gpu_launches). */
+int hm_forward_launch_count(const hm_ctx* ctx);
+/* Library / build identification string. */
+const char* hm_version(void);
+
+/* ---- test hooks (used by tests/ only; same kernels as the hot path) ----------------------------
+ * C[M,N] = A[M,K] * W[N,K]^T with the fused epilogue `epi` (0 bias->fp16, 1 bias+GELU->fp16,
+ * 2 bias + residual add into f32 out, 3 bias + pos[(m % 192), n] -> f32).  A: DEVICE fp16 bits,
+ * W: DEVICE bf16 bits (w_format 1) or fp16 bits (w_format 0), bias/pos: DEVICE f32,
+ * out: DEVICE fp16 (epi 0,1) or f32 (epi 2,3). */
+int hm_test_gemm(hm_ctx* ctx, int cta_group, int bn, int epi, int w_format, const uint16_t* A,
+                 const uint16_t* W, const float* bias, const float* pos, void* out, int M, int N,
+                 int K, void* stream);
+/* y = LayerNorm(x) over rows of 1280 (out_f16 != 0: fp16 output, else f32) */
+int hm_test_layernorm(hm_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y,
+                      int rows, float eps, int out_f16, void* stream);
+/* attention core on a [B*192,3840] fp16 qkv buffer -> [B*192,1280] fp16 */
+int hm_test_attention(hm_ctx* ctx, const uint16_t* qkv, uint16_t* out, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAMER_B200_H */
