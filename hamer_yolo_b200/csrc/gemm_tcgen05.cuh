@@ -1,9 +1,9 @@
-// fp16 (activations) x bf16 (weights) -> f32 GEMM for the ViT-H backbone:
-//   C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
-// Activations are fp16 rather than bf16 because the 0.5 mm / 1e-3 parity bar needs the 11-bit
+// fp16 x fp16 -> f32 GEMM for the ViT-H backbone:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+// Operands are fp16 rather than bf16 because the 0.5 mm / 1e-3 parity bar needs the 11-bit
 // mantissa (tests/tools/emulate_bf16.py: bf16 activations give 1.9e-3 on the rotation matrices,
-// fp16 3e-4); weights stay bf16 (the checkpoint values are bf16-representable); the products are
-// exact in the fp32 accumulator either way and the tensor-pipe rate is the same (kind::f16).
+// fp16 3e-4).  tcgen05.mma kind::f16 runs fp16 and bf16 at the same rate but needs A and B of the
+// same type (a mixed fp16 x bf16 descriptor raises an illegal-instruction fault on B200 - measured),
+// so the weights are fp16 as well; every product is exact in the fp32 accumulator.
 //
 // Replaces every nn.Linear / the patch-embed Conv2d of the reference backbone
 // (hamer/hamer/models/backbones/vit.py:77-79 fc1/fc2, :104 qkv, :107 proj, :168 patch-embed conv),
@@ -40,7 +40,7 @@ struct GemmParams {
     int M, N, K;
     const float* bias;  // [N]
     void* out;          // [M, ldo] fp16 or f32
-    uint32_t b_format;  // weight operand format: 1 = bf16 (default), 0 = fp16
+    uint32_t b_format;  // operand format of A and B: 0 = fp16 (the hot path), 1 = bf16
     int ldo;            // elements
     const float* pos;   // [pos_rows, N] (EPI_BIAS_POS_F32)
     int pos_rows;
@@ -162,7 +162,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===================== MMA issuer (leader CTA, one lane) =====================
         if (is_leader && lane == 0) {
             const uint32_t idesc =
-                ptx::make_idesc_f16kind_f32(/*A fp16*/ 0, (int)p.b_format, GEMM_BM * CTA_GROUP, BN);
+                ptx::make_idesc_f16kind_f32((int)p.b_format, (int)p.b_format, GEMM_BM * CTA_GROUP, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;

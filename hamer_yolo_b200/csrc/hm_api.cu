@@ -94,7 +94,7 @@ struct hm_ctx {
 
     // workspace (max_batch)
     __half *patches = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;  // fp16 activations
-    uint32_t b_format = 1;   // weight operand format of the backbone GEMMs: 1 = bf16, 0 = fp16
+    uint32_t b_format = 0;   // operand format of the backbone GEMMs (A and B): 0 = fp16, 1 = bf16
     float *x = nullptr, *feats = nullptr;
     CUtensorMap tm_patches, tm_xn, tm_att, tm_h;
     // decoder workspace
@@ -388,7 +388,7 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     c->num_sms = prop.multiProcessorCount;
     c->plan.cta_group = (cfg->gemm_cta_group == 1) ? 1 : 2;
     c->plan.bn = 256;
-    c->b_format = cfg->weights_f16 ? 0u : 1u;
+    c->b_format = 0u;   // fp16 weight operands (kind::f16 requires A and B of the same 16-bit type)
     if (!get_tmap_encode()) return bail(HM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
     const size_t Mmax = (size_t)cfg->max_batch * TOK, Bm = (size_t)cfg->max_batch;
@@ -474,7 +474,7 @@ int hm_set_weight(hm_ctx* c, const char* name, const float* data, const int64_t*
     HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.f32), t.numel * 4));
     HM_CUDA(c, cudaMemcpy(t.f32, data, t.numel * 4, cudaMemcpyHostToDevice));
     if (is_backbone_matrix(key)) {
-        // tensor-core operand: keep only the bf16 copy
+        // tensor-core operand: keep only the 16-bit (fp16) copy
         HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.bf16), t.numel * 2));
         f32_to_w16_kernel<<<(unsigned)((t.numel + 255) / 256), 256>>>(
             t.f32, reinterpret_cast<uint16_t*>(t.bf16), t.numel, (int)c->b_format);

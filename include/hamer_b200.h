@@ -40,8 +40,7 @@ typedef struct hm_config {
     int32_t max_batch;        /* largest B of hm_forward / n of hm_preprocess */
     int32_t max_frame_bytes;  /* largest H*row_stride accepted by hm_preprocess (host frames) */
     int32_t gemm_cta_group;   /* 0 = default (2: CTA-pair UMMA M=256), 1 = single-CTA tiles */
-    int32_t weights_f16;      /* 0 = backbone weights as bf16 operands (default), 1 = as fp16 */
-    int32_t reserved[4];
+    int32_t reserved[5];
 } hm_config;
 
 /* Device pointers of the tensors HAMER.forward_step returns (hamer/hamer/models/hamer.py:124-156).
@@ -70,8 +69,8 @@ const char* hm_last_error(const hm_ctx* ctx);   /* ctx may be NULL: last hm_crea
  * One call per state-dict entry of the reference checkpoint (key layout: SURVEY.md section 5;
  * e.g. "backbone.blocks.0.attn.qkv.weight", "mano_head.transformer.transformer.layers.0.1.fn.to_kv.weight",
  * "mano_head.init_hand_pose").  `data` is a HOST pointer to float32 values in the reference's own
- * layout; matrices used by the backbone GEMMs are converted to bf16 once (they must be
- * bf16-representable for the 0.5 mm parity bar).  Replaces
+ * layout; matrices used by the backbone GEMMs are converted to fp16 once (tensor-core operands,
+ * fp32 accumulation; precision budget in DESIGN.md).  Replaces
  * HAMER.load_from_checkpoint(..., strict=False) (models/__init__.py:46). */
 int hm_set_weight(hm_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
 /* Checks that every tensor is present and builds the fused tables (positional table, decoder
@@ -124,7 +123,7 @@ const char* hm_version(void);
 /* ---- test hooks (used by tests/ only; same kernels as the hot path) ----------------------------
  * C[M,N] = A[M,K] * W[N,K]^T with the fused epilogue `epi` (0 bias->fp16, 1 bias+GELU->fp16,
  * 2 bias + residual add into f32 out, 3 bias + pos[(m % 192), n] -> f32).  A: DEVICE fp16 bits,
- * W: DEVICE bf16 bits (w_format 1) or fp16 bits (w_format 0), bias/pos: DEVICE f32,
+ * W: DEVICE fp16 bits (w_format 0; 1 = both operands bf16), bias/pos: DEVICE f32,
  * out: DEVICE fp16 (epi 0,1) or f32 (epi 2,3). */
 int hm_test_gemm(hm_ctx* ctx, int cta_group, int bn, int epi, int w_format, const uint16_t* A,
                  const uint16_t* W, const float* bias, const float* pos, void* out, int M, int N,

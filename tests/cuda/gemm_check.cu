@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
     int cg = atoi(argv[1]), bn = atoi(argv[2]), epi = atoi(argv[3]);
     int M = atoi(argv[4]), N = atoi(argv[5]), K = atoi(argv[6]);
     int iters = argc > 7 ? atoi(argv[7]) : 10;
-    int w_fmt = argc > 8 ? atoi(argv[8]) : 1;
+    int w_fmt = argc > 8 ? atoi(argv[8]) : 0;
     int dev = 0;
     cudaDeviceProp prop;
     CK(cudaSetDevice(dev));

@@ -48,7 +48,7 @@ def test_gemm_epilogues(engine, cta_group, epi, M, N, K):
     dev = engine.device
     g = torch.Generator(device=dev).manual_seed(M + N + K + epi)
     A = (torch.randn(M, K, generator=g, device=dev) * 0.5).half()
-    W = (torch.randn(N, K, generator=g, device=dev) * 0.03).bfloat16()
+    W = (torch.randn(N, K, generator=g, device=dev) * 0.03).half()
     bias = torch.randn(N, generator=g, device=dev)
     pos = torch.randn(192, N, generator=g, device=dev)
     acc = A.float() @ W.float().t() + bias
@@ -58,7 +58,7 @@ def test_gemm_epilogues(engine, cta_group, epi, M, N, K):
     else:
         out = torch.randn(M, N, generator=g, device=dev)
         ref = acc + (out if epi == 2 else pos[torch.arange(M, device=dev) % 192])
-    engine.check(engine.lib.hm_test_gemm(engine.h, cta_group, 256, epi, 1, C.c_void_p(A.data_ptr()),
+    engine.check(engine.lib.hm_test_gemm(engine.h, cta_group, 256, epi, 0, C.c_void_p(A.data_ptr()),
                                          C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()),
                                          C.c_void_p(pos.data_ptr()), C.c_void_p(out.data_ptr()), M, N, K,
                                          engine.stream()))
