@@ -31,8 +31,11 @@ class HmError(RuntimeError):
 # every symbol include/hamer_b200.h declares (tests check the library exports all of them)
 EXPORTS = ('hm_create', 'hm_destroy', 'hm_last_error', 'hm_set_weight', 'hm_finalize_weights',
            'hm_set_mano', 'hm_preprocess', 'hm_forward', 'hm_backbone', 'hm_mano_head',
-           'hm_mano_lbs', 'hm_forward_launch_count', 'hm_version', 'hm_test_gemm',
-           'hm_test_layernorm', 'hm_test_attention')
+           'hm_mano_lbs', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
+           'hm_profile_collect', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention')
+
+PROFILE_CATEGORIES = ('im2col', 'gemm_patch', 'layernorm', 'gemm_qkv', 'attention', 'gemm_proj',
+                      'gemm_fc1', 'gemm_fc2', 'head', 'mano_lbs', 'crop')
 
 _lib = None
 
@@ -63,7 +66,9 @@ def load():
     lib.hm_forward_launch_count.argtypes = [vp]
     lib.hm_version.argtypes = []
     lib.hm_version.restype = C.c_char_p
-    lib.hm_test_gemm.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.hm_profile_enable.argtypes = [vp, i32]
+    lib.hm_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32), i32]
+    lib.hm_test_gemm.argtypes =[vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.hm_test_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, i32, vp]
     lib.hm_test_attention.argtypes = [vp, vp, vp, i32, vp]
     for name in EXPORTS:

@@ -5,7 +5,7 @@
 // the tcgen05 GEMMs in gemm_tcgen05.cuh; this kernel is 2.4 % of the block's FLOPs.
 //
 // One CTA per (head, crop): Q, K, V (192 x 80 fp16 each) are staged in shared memory with
-// cp.async, 12 warps each own 16 query rows.  S = Q K^T and O = P V run on the tensor cores
+// cp.async, 6 warps each own 2 x 16 query rows (two CTAs per SM so one's loads overlap the other's MMAs).  S = Q K^T and O = P V run on the tensor cores
 // (mma.sync m16n8k16 fp16 -> fp32); scores, max, exp and the row sum stay in fp32 registers;
 // P is rounded to fp16 only as the MMA operand.  O is staged back through the warp's own Q rows so
 // the global store is 16-byte coalesced.
@@ -21,7 +21,7 @@ namespace hm {
 constexpr int ATT_T = 192;
 constexpr int ATT_D = 80;
 constexpr int ATT_PITCH = 88;  // fp16 elements per smem row: 176 B keeps ldmatrix conflict-free
-constexpr int ATT_THREADS = 384;
+constexpr int ATT_THREADS = 192;   // 6 warps x 2 query tiles of 16 rows; 2 CTAs per SM overlap load and math
 constexpr int ATT_SMEM_BYTES = 3 * ATT_T * ATT_PITCH * 2;
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 vit_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                      float scale_log2e) {
     extern __shared__ __align__(16) uint8_t att_smem[];
@@ -68,11 +68,13 @@ vit_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    const int m0 = warp * 16;
     const uint32_t q_addr = sbase;
     const uint32_t k_addr = sbase + ATT_T * ATT_PITCH * 2;
     const uint32_t v_addr = k_addr + ATT_T * ATT_PITCH * 2;
 
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int m0 = (warp * 2 + mt) * 16;
     // ---- S = Q K^T  (16 x 192 per warp: 24 n-tiles of 8) ----------------------------------------
     float s[24][4];
 #pragma unroll
@@ -159,6 +161,7 @@ vit_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
         const uint4 v = *reinterpret_cast<const uint4*>(sQ + (m0 + r) * ATT_PITCH + ch * 8);
         *reinterpret_cast<uint4*>(obase + (size_t)r * 1280 + ch * 8) = v;
     }
+  }  // mt
 }
 
 }  // namespace hm

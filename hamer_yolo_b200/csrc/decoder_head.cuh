@@ -40,6 +40,22 @@ constexpr int SK_ROWS = 64;   // crops per block tile
 constexpr int SK_COLS = 8;    // output columns (warps) per block
 constexpr int SK_KC = 128;    // K chunk staged in smem
 
+// Reduce 32 per-lane partial sums for 32 rows at once: afterwards lane i holds the full sum of row i
+// (31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+            const float keep = up ? v[j + o] : v[j];
+            const float send = up ? v[j] : v[j + o];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(SK_COLS * 32)
 skinny_linear_kernel(const SkinnyParams p) {
@@ -53,46 +69,68 @@ skinny_linear_kernel(const SkinnyParams p) {
     float* Y = p.Y + z * p.y_bs;
     const int rows = min(SK_ROWS, p.B - b0);
     const bool active = n < p.N;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     float acc[SK_ROWS];
 #pragma unroll
     for (int i = 0; i < SK_ROWS; ++i) acc[i] = 0.f;
 
-    for (int k0 = 0; k0 < p.K; k0 += SK_KC) {
-        const int kc = min(SK_KC, p.K - k0);          // 128 or 64
-        const int kc4 = kc >> 2;
-        __syncthreads();
-        for (int e = threadIdx.x; e < rows * kc4; e += blockDim.x) {
-            const int r = e / kc4, c = e % kc4;
-            reinterpret_cast<float4*>(&xs[r][0])[c] =
-                *reinterpret_cast<const float4*>(X + (size_t)(b0 + r) * p.ldx + k0 + c * 4);
-        }
-        __syncthreads();
-        if (active && lane < kc4) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * p.K + k0) + lane);
+    // software pipeline: the next chunk's X tile (8 float4 per thread) and W slice are in flight
+    // while the current chunk is multiplied out of shared memory.  Tile rows >= rows and columns
+    // >= the chunk width are zero-filled so the inner loop has no predicates.
+    float4 xr[SK_ROWS / 8];
+    float4 wn;
+    auto fetch = [&](int k0) {
+        const int kc4 = min(SK_KC, p.K - k0) >> 2;
 #pragma unroll
-            for (int r = 0; r < SK_ROWS; ++r) {
-                if (r < rows) {
-                    const float4 x = reinterpret_cast<const float4*>(&xs[r][0])[lane];
-                    acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
-                }
-            }
+        for (int i = 0; i < SK_ROWS / 8; ++i) {
+            const int r = warp + 8 * i;
+            xr[i] = (lane < kc4 && r < rows)
+                        ? *reinterpret_cast<const float4*>(X + (size_t)(b0 + r) * p.ldx + k0 + lane * 4)
+                        : zero4;
+        }
+        wn = (active && lane < kc4)
+                 ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * p.K + k0) + lane) : zero4;
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += SK_KC) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SK_ROWS / 8; ++i)
+            reinterpret_cast<float4*>(&xs[warp + 8 * i][0])[lane] = xr[i];
+        const float4 w = wn;
+        __syncthreads();
+        if (k0 + SK_KC < p.K) fetch(k0 + SK_KC);
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r) {
+            const float4 x = reinterpret_cast<const float4*>(&xs[r][0])[lane];
+            acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
         }
     }
+    // lane i ends up with the dot products of rows i and i + 32
+    float lo[32], hi[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { lo[i] = acc[i]; hi[i] = acc[i + 32]; }
+    float v0 = warp_transpose_reduce32(lo, lane);
+    float v1 = warp_transpose_reduce32(hi, lane);
     if (!active) return;
     const float bias = p.bias ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
-#pragma unroll
-    for (int r = 0; r < SK_ROWS; ++r) {
-        if (r < rows) {                                 // warp-uniform
-            float v = warp_sum(acc[r]) * p.scale + bias;
-            if constexpr (EPI == SK_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-            if (lane == 0) {
-                float* y = Y + (size_t)(b0 + r) * p.ldy + n;
-                if constexpr (EPI == SK_RESID) v += *y;
-                *y = v;
-            }
-        }
+    v0 = v0 * p.scale + bias;
+    v1 = v1 * p.scale + bias;
+    if constexpr (EPI == SK_GELU) {
+        v0 = 0.5f * v0 * (1.0f + erff(v0 * 0.70710678118654752440f));
+        v1 = 0.5f * v1 * (1.0f + erff(v1 * 0.70710678118654752440f));
     }
+    float* y0 = Y + (size_t)(b0 + lane) * p.ldy + n;
+    float* y1 = Y + (size_t)(b0 + lane + 32) * p.ldy + n;
+    const bool ok0 = lane < rows, ok1 = lane + 32 < rows;
+    if constexpr (EPI == SK_RESID) {
+        const float r0 = ok0 ? *y0 : 0.f, r1 = ok1 ? *y1 : 0.f;     // both loads in flight together
+        v0 += r0;
+        v1 += r1;
+    }
+    if (ok0) *y0 = v0;
+    if (ok1) *y1 = v1;
 }
 
 // ------------------------------------------------------------------------------------------------

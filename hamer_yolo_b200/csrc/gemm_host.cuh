@@ -42,15 +42,32 @@ inline bool make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows,
     return r == CUDA_SUCCESS;
 }
 
+// fp32 output matrix [rows, cols] for the TMA reduce-add epilogue: box = 32 x 32 floats
+// (128-byte rows, 128B swizzle to match the epilogue's XOR-swizzled staging tile).
+inline bool make_tmap_f32_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t ld) {
+    PFN_tmapEncodeTiled enc = get_tmap_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 struct GemmPlan {
     int cta_group;  // 1 or 2
     int bn;         // 128 or 256
 };
 
 template <int CTA_GROUP, int BN, int EPI>
-inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                                 const GemmParams& p,
                                  int num_sms, cudaStream_t stream) {
-    using Cfg = GemmCfg<CTA_GROUP, BN>;
+    using Cfg = GemmCfg<CTA_GROUP, BN, EPI>;
     auto kern = gemm_bf16_tn_kernel<CTA_GROUP, BN, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -65,7 +82,7 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
     if (tiles < workers) workers = tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * CTA_GROUP);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -75,29 +92,32 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p);
 }
 
 template <int CTA_GROUP, int BN>
 inline cudaError_t gemm_launch_e(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                                 const GemmParams& p, int num_sms, cudaStream_t s) {
+                                 const CUtensorMap& tout, const GemmParams& p, int num_sms,
+                                 cudaStream_t s) {
     switch (epi) {
-        case EPI_BIAS_BF16: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_BF16>(ta, tb, p, num_sms, s);
-        case EPI_BIAS_GELU_BF16: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_GELU_BF16>(ta, tb, p, num_sms, s);
-        case EPI_BIAS_RESID_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_RESID_F32>(ta, tb, p, num_sms, s);
-        case EPI_BIAS_POS_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_POS_F32>(ta, tb, p, num_sms, s);
+        case EPI_BIAS_BF16: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_BF16>(ta, tb, tout, p, num_sms, s);
+        case EPI_BIAS_GELU_BF16: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_GELU_BF16>(ta, tb, tout, p, num_sms, s);
+        case EPI_BIAS_RESID_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_RESID_F32>(ta, tb, tout, p, num_sms, s);
+        case EPI_BIAS_POS_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_POS_F32>(ta, tb, tout, p, num_sms, s);
     }
     return cudaErrorInvalidValue;
 }
 
-// The W tensor map's box rows must equal BN / cta_group (see GemmCfg::B_ROWS).
+// The W tensor map's box rows must equal BN / cta_group (see GemmCfg::B_ROWS).  `tout` is the fp32
+// output map of the residual epilogue (make_tmap_f32_out); other epilogues ignore it (pass ta).
 inline cudaError_t gemm_launch(GemmPlan plan, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                               const GemmParams& p, int num_sms, cudaStream_t s) {
+                               const CUtensorMap& tout, const GemmParams& p, int num_sms,
+                               cudaStream_t s) {
     if (p.K % GEMM_BK != 0 || p.N % plan.bn != 0) return cudaErrorInvalidValue;
-    if (plan.cta_group == 1 && plan.bn == 256) return gemm_launch_e<1, 256>(epi, ta, tb, p, num_sms, s);
-    if (plan.cta_group == 1 && plan.bn == 128) return gemm_launch_e<1, 128>(epi, ta, tb, p, num_sms, s);
-    if (plan.cta_group == 2 && plan.bn == 256) return gemm_launch_e<2, 256>(epi, ta, tb, p, num_sms, s);
-    if (plan.cta_group == 2 && plan.bn == 128) return gemm_launch_e<2, 128>(epi, ta, tb, p, num_sms, s);
+    if (plan.cta_group == 1 && plan.bn == 256) return gemm_launch_e<1, 256>(epi, ta, tb, tout, p, num_sms, s);
+    if (plan.cta_group == 1 && plan.bn == 128) return gemm_launch_e<1, 128>(epi, ta, tb, tout, p, num_sms, s);
+    if (plan.cta_group == 2 && plan.bn == 256) return gemm_launch_e<2, 256>(epi, ta, tb, tout, p, num_sms, s);
+    if (plan.cta_group == 2 && plan.bn == 128) return gemm_launch_e<2, 128>(epi, ta, tb, tout, p, num_sms, s);
     return cudaErrorInvalidValue;
 }
 

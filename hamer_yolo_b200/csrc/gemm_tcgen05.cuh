@@ -11,7 +11,8 @@
 //
 // sm_100a design
 //   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one lane),
-//     warps 2..9 = epilogue (TMEM -> registers -> global).
+//     warps 2.. = epilogue (TMEM -> registers -> global): 8 warps, 16 for the GELU epilogue whose
+//     erf evaluation is issue-bound.
 //   * operands: TMA 128B-swizzled K-major tiles, BK = 64 (one swizzle atom per row), STAGES-deep
 //     mbarrier ring.
 //   * accumulators: fp32 in TMEM, two stages (2 x BN columns) so the epilogue of tile i overlaps the
@@ -19,8 +20,14 @@
 //   * CTA_GROUP == 2: a CTA pair (cluster 2x1x1) computes a 256 x BN tile with UMMA M = 256; each
 //     CTA loads its own 128 rows of A and half (BN/2 rows) of W, the leader CTA issues the MMAs,
 //     tcgen05.commit multicasts the "slot free" / "accumulator full" signals to both CTAs.
-//   * epilogues (template EPI): bias -> bf16 | bias + exact-erf GELU -> bf16 |
+//   * epilogues (template EPI): bias -> fp16 | bias + erf-GELU -> fp16 |
 //     bias + residual add into the fp32 stream | bias + positional table -> fp32.
+//     The residual epilogue never reads the stream: each warp writes its 32x32 (acc + bias) block
+//     into a 128B-swizzled shared-memory tile and issues a TMA reduce-add (cp.reduce.async.bulk
+//     .add.f32), so x += tile happens at L2 and the SM only produces write traffic (the plain
+//     read-modify-write version was bound by the latency of re-reading x: 34 % tensor-pipe
+//     utilisation at K = 1280).  The positional epilogue (patch embed, 0.15 % of the FLOPs)
+//     transposes through the same tile for 128-byte coalesced stores.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -47,25 +54,46 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BM = 128;  // rows per CTA (UMMA M = 128 * CTA_GROUP)
-constexpr int GEMM_BK = 64;   // 64 bf16 = 128 B = one swizzle atom row
+constexpr int GEMM_BK = 64;   // 64 x 16-bit = 128 B = one swizzle atom row
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr uint32_t GEMM_SMEM_LIMIT = 227 * 1024;
 
-template <int CTA_GROUP, int BN>
+template <int CTA_GROUP, int BN, int EPI>
 struct GemmCfg {
-    static constexpr int B_ROWS = BN / CTA_GROUP;  // rows of W each CTA loads per stage
+    static constexpr bool F32_OUT = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_POS_F32);
+    static constexpr int EPI_WARPS = (EPI == EPI_BIAS_GELU_BF16) ? 16 : 8;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int COL_PARTS = EPI_WARPS / 4;             // warps sharing one TMEM lane quadrant
+    static constexpr int COLS_PER_WARP = BN / COL_PARTS;
+    static constexpr int B_ROWS = BN / CTA_GROUP;               // rows of W each CTA loads per stage
     static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr uint32_t B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-    static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two >= 32)
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    // fp32 epilogues stage 32x32 blocks per warp (double-buffered for the TMA reduce-add path)
+    static constexpr uint32_t STAGING_BYTES = F32_OUT ? EPI_WARPS * 2 * 32 * 32 * 4 : 0;
+    static constexpr uint32_t FIXED_BYTES = 1024 /*align*/ + 256 /*barriers*/ + STAGING_BYTES;
+    static constexpr int STAGES_FIT = (GEMM_SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT >= 8 ? 8 : STAGES_FIT;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;               // two accumulator stages
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
     static_assert(TMEM_COLS == 512 || TMEM_COLS == 256 || TMEM_COLS == 128, "TMEM cols");
+    static_assert(STAGES >= 3, "pipeline too shallow");
+    static_assert(COLS_PER_WARP % 32 == 0, "epilogue chunking");
 };
 
+// erf-GELU as nn.GELU() computes it, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz-Stegun
+// 7.1.26 (|error| <= 1.5e-7 absolute - three orders below the fp16 rounding of the result) instead
+// of erff(): ~14 issue slots instead of ~25, which is what bounds the fc1 epilogue.
 __device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = exp2f(-1.4426950408889634f * z * z);
+    const float erf_abs = fmaf(-poly * t, e, 1.0f);             // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
@@ -74,10 +102,11 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
 }
 
 template <int CTA_GROUP, int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<CTA_GROUP, BN, EPI>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using Cfg = GemmCfg<CTA_GROUP, BN>;
+                    const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+    using Cfg = GemmCfg<CTA_GROUP, BN, EPI>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
@@ -88,7 +117,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);   // 1024-aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]  TMA bytes landed (leader CTA's is used)
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMAs that read the slot retired
     uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       accumulator stage complete
@@ -111,13 +141,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
+        if constexpr (EPI == EPI_BIAS_RESID_F32) ptx::prefetch_tmap(&tmap_out);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], GEMM_EPI_WARPS * CTA_GROUP);
+            ptx::mbar_init(&tmem_empty[s], Cfg::EPI_WARPS * CTA_GROUP);
         }
         ptx::fence_mbar_init();
     }
@@ -199,27 +230,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===================== epilogue warps =====================
         const int ew = warp - 2;
         const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;               // which half of the BN columns
-        constexpr int COLS_PER_WARP = BN / 2;
+        const int part = ew >> 2;               // which slice of the BN columns
+        constexpr int COLS_PER_WARP = Cfg::COLS_PER_WARP;
+        float* st = staging + ew * 2048;        // this warp's two 32x32 fp32 tiles (F32_OUT only)
+        uint32_t chunk_no = 0;                  // running count of staged chunks (double buffering)
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
             const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-            const int row = m_blk * tile_m + (int)cta_rank * GEMM_BM + quad * 32 + lane;
-            const int col0 = n_blk * BN + half * COLS_PER_WARP;
+            const int row0 = m_blk * tile_m + (int)cta_rank * GEMM_BM + quad * 32;
+            const int row = row0 + lane;
+            const int col0 = n_blk * BN + part * COLS_PER_WARP;
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                    (uint32_t)(acc * BN + half * COLS_PER_WARP);
+                                    (uint32_t)(acc * BN + part * COLS_PER_WARP);
 #pragma unroll 1
             for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(t_addr + (uint32_t)(c * 32), r);
                 ptx::tmem_ld_wait();
                 const int col = col0 + c * 32;
-                if (row < p.M) {
-                    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
-                    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                if constexpr (!Cfg::F32_OUT) {
+                    if (row < p.M) {
+                        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
                         __half* out = reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -243,24 +277,54 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             o.w = pack_act2(v[6], v[7]);
                             *reinterpret_cast<uint4*>(out + j * 8) = o;
                         }
-                    } else {
-                        float* out = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
-                        const float* pos = nullptr;
-                        if constexpr (EPI == EPI_BIAS_POS_F32)
-                            pos = p.pos + (size_t)(row % p.pos_rows) * p.N + col;
+                    }
+                } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                    // (acc + bias) -> 128B-swizzled smem tile -> TMA reduce-add into the stream
+                    float* buf = st + (chunk_no & 1u) * 1024;
+                    if (chunk_no >= 2) {                 // the TMA that read this buffer has drained
+                        if (lane == 0) ptx::bulk_wait_read<1>();
+                        __syncwarp();
+                    }
+                    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b = __ldg(bias4 + j);
-                            float4 x;
-                            if constexpr (EPI == EPI_BIAS_RESID_F32)
-                                x = *reinterpret_cast<const float4*>(out + j * 4);
-                            else
-                                x = __ldg(reinterpret_cast<const float4*>(pos + j * 4));
-                            x.x += __uint_as_float(r[j * 4 + 0]) + b.x;
-                            x.y += __uint_as_float(r[j * 4 + 1]) + b.y;
-                            x.z += __uint_as_float(r[j * 4 + 2]) + b.z;
-                            x.w += __uint_as_float(r[j * 4 + 3]) + b.w;
-                            *reinterpret_cast<float4*>(out + j * 4) = x;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(bias4 + j);
+                        float4 v;
+                        v.x = __uint_as_float(r[j * 4 + 0]) + b.x; v.y = __uint_as_float(r[j * 4 + 1]) + b.y;
+                        v.z = __uint_as_float(r[j * 4 + 2]) + b.z; v.w = __uint_as_float(r[j * 4 + 3]) + b.w;
+                        *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+                    }
+                    ptx::fence_proxy_async();            // generic-proxy writes -> visible to TMA
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < p.M) ptx::tma_reduce_add_2d(&tmap_out, buf, col, row0);
+                        ptx::bulk_commit();
+                    }
+                    ++chunk_no;
+                } else {
+                    // thread = accumulator row  ->  XOR-swizzled smem tile  ->  lane = 4 columns
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v;
+                        v.x = __uint_as_float(r[j * 4 + 0]); v.y = __uint_as_float(r[j * 4 + 1]);
+                        v.z = __uint_as_float(r[j * 4 + 2]); v.w = __uint_as_float(r[j * 4 + 3]);
+                        *reinterpret_cast<float4*>(st + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+                    }
+                    __syncwarp();
+                    const int c4 = lane & 7;            // float4 column inside the 32-column chunk
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col) + c4);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + (lane >> 3);
+                        const int grow = row0 + rr;
+                        if (grow < p.M) {
+                            const float4 a = *reinterpret_cast<const float4*>(st + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                            float* out = reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + col + c4 * 4;
+                            float4 x = __ldg(reinterpret_cast<const float4*>(
+                                p.pos + (size_t)(grow % p.pos_rows) * p.N + col + c4 * 4));
+                            x.x += a.x + b.x; x.y += a.y + b.y; x.z += a.z + b.z; x.w += a.w + b.w;
+                            *reinterpret_cast<float4*>(out) = x;
                         }
                     }
                 }
@@ -274,6 +338,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
+        }
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            if (lane == 0) ptx::bulk_wait_all();        // all reduce-adds have landed in global memory
         }
     }
 

@@ -97,6 +97,7 @@ struct hm_ctx {
     uint32_t b_format = 0;   // operand format of the backbone GEMMs (A and B): 0 = fp16, 1 = bf16
     float *x = nullptr, *feats = nullptr;
     CUtensorMap tm_patches, tm_xn, tm_att, tm_h;
+    CUtensorMap tm_x_out;   // fp32 residual stream as the target of the TMA reduce-add epilogue
     // decoder workspace
     float *hx = nullptr, *hy = nullptr, *hv = nullptr, *hq = nullptr, *hu = nullptr, *hsc = nullptr,
           *hpool = nullptr, *ho = nullptr, *hh = nullptr, *hraw = nullptr, *hrot = nullptr,
@@ -115,9 +116,43 @@ struct hm_ctx {
     bool crop_event_pending = false;
 
     std::vector<void*> allocs;
+
+    // optional per-category timing (hm_profile_*): CUDA events recorded on the launch stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
+    struct ProfSpan { int cat; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_spans;
+};
+
+// RAII bracket around one launch (or one group of launches) of category `cat`
+struct ProfScope {
+    hm_ctx* c; cudaStream_t s; int cat; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t take(hm_ctx* c) {
+        if (c->prof_used == c->prof_pool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            c->prof_pool.push_back(e);
+        }
+        return c->prof_pool[c->prof_used++];
+    }
+    ProfScope(hm_ctx* c_, cudaStream_t s_, int cat_) : c(c_), s(s_), cat(cat_) {
+        if (!c->prof_on) return;
+        a = take(c); b = take(c);
+        if (a) cudaEventRecord(a, s);
+    }
+    ~ProfScope() {
+        if (!c->prof_on || !a || !b) return;
+        cudaEventRecord(b, s);
+        c->prof_spans.push_back({cat, a, b});
+    }
 };
 
 namespace {
+
+// profiling categories (order documented in include/hamer_b200.h: hm_profile_collect)
+enum ProfCat : int { PC_IM2COL = 0, PC_GEMM_PATCH, PC_LAYERNORM, PC_GEMM_QKV, PC_ATTENTION, PC_GEMM_PROJ,
+                     PC_GEMM_FC1, PC_GEMM_FC2, PC_HEAD, PC_MANO_LBS, PC_CROP, PC_COUNT };
 
 int fail(hm_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
@@ -266,33 +301,39 @@ int run_gemm(hm_ctx* c, int epi, const CUtensorMap& ta, const CUtensorMap& tb, i
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
     p.b_format = c->b_format;
-    HM_CUDA(c, gemm_launch(c->plan, epi, ta, tb, p, c->num_sms, s));
+    HM_CUDA(c, gemm_launch(c->plan, epi, ta, tb, c->tm_x_out, p, c->num_sms, s));
     return HM_OK;
 }
 
 int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStream_t s) {
     const int M = B * TOK;
     const float att_scale = 0.11180339887498948f * 1.4426950408889634f;   // 80^-0.5 * log2(e)
-    im2col_patch16_kernel<<<dim3(16, B), 256, 0, s>>>(img, c->patches, B);
-    int rc = run_gemm(c, EPI_BIAS_POS_F32, c->tm_patches, c->tm_wpatch, M, DM, KPATCH, c->b_patch,
-                      c->x, c->pos_tab, s);
-    if (rc) return rc;
+    int rc;
+    { ProfScope ps(c, s, PC_IM2COL); im2col_patch16_kernel<<<dim3(16, B), 256, 0, s>>>(img, c->patches, B); }
+    { ProfScope ps(c, s, PC_GEMM_PATCH);
+      if ((rc = run_gemm(c, EPI_BIAS_POS_F32, c->tm_patches, c->tm_wpatch, M, DM, KPATCH, c->b_patch, c->x, c->pos_tab, s))) return rc; }
     for (int i = 0; i < DEPTH; ++i) {
         const BlockW& w = c->blk[i];
-        launch_ln<10, __half>(c->x, w.ln1_g, w.ln1_b, c->xn, M, 1e-6f, s);
-        if ((rc = run_gemm(c, EPI_BIAS_BF16, c->tm_xn, w.tm_qkv, M, 3 * DM, DM, w.b_qkv, c->qkv, nullptr, s))) return rc;
-        vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(c->qkv, c->att, att_scale);
-        if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_att, w.tm_proj, M, DM, DM, w.b_proj, c->x, nullptr, s))) return rc;
-        launch_ln<10, __half>(c->x, w.ln2_g, w.ln2_b, c->xn, M, 1e-6f, s);
-        if ((rc = run_gemm(c, EPI_BIAS_GELU_BF16, c->tm_xn, w.tm_fc1, M, DFF, DM, w.b_fc1, c->hbuf, nullptr, s))) return rc;
-        if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_h, w.tm_fc2, M, DM, DFF, w.b_fc2, c->x, nullptr, s))) return rc;
+        { ProfScope ps(c, s, PC_LAYERNORM); launch_ln<10, __half>(c->x, w.ln1_g, w.ln1_b, c->xn, M, 1e-6f, s); }
+        { ProfScope ps(c, s, PC_GEMM_QKV);
+          if ((rc = run_gemm(c, EPI_BIAS_BF16, c->tm_xn, w.tm_qkv, M, 3 * DM, DM, w.b_qkv, c->qkv, nullptr, s))) return rc; }
+        { ProfScope ps(c, s, PC_ATTENTION);
+          vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(c->qkv, c->att, att_scale); }
+        { ProfScope ps(c, s, PC_GEMM_PROJ);
+          if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_att, w.tm_proj, M, DM, DM, w.b_proj, c->x, nullptr, s))) return rc; }
+        { ProfScope ps(c, s, PC_LAYERNORM); launch_ln<10, __half>(c->x, w.ln2_g, w.ln2_b, c->xn, M, 1e-6f, s); }
+        { ProfScope ps(c, s, PC_GEMM_FC1);
+          if ((rc = run_gemm(c, EPI_BIAS_GELU_BF16, c->tm_xn, w.tm_fc1, M, DFF, DM, w.b_fc1, c->hbuf, nullptr, s))) return rc; }
+        { ProfScope ps(c, s, PC_GEMM_FC2);
+          if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_h, w.tm_fc2, M, DM, DFF, w.b_fc2, c->x, nullptr, s))) return rc; }
     }
-    launch_ln<10, float>(c->x, c->lnf_g, c->lnf_b, feats_out, M, 1e-6f, s);
+    { ProfScope ps(c, s, PC_LAYERNORM); launch_ln<10, float>(c->x, c->lnf_g, c->lnf_b, feats_out, M, 1e-6f, s); }
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
 }
 
 int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaStream_t s) {
+    ProfScope ps(c, s, PC_HEAD);
     head_init_token_kernel<<<(B * HD + 255) / 256, 256, 0, s>>>(c->tok0, c->hx, B);
     const float scale = 0.125f;   // dim_head ** -0.5 = 64^-0.5
     for (int l = 0; l < HDEPTH; ++l) {
@@ -346,6 +387,7 @@ int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* c
     a.kp2d = (cam_t != nullptr) ? kp2d : nullptr;
     a.focal_over_size = 5000.0f / 256.0f;
     a.B = B;
+    ProfScope ps(c, s, PC_MANO_LBS);
     mano_lbs_kernel<<<(B + LBS_HANDS - 1) / LBS_HANDS, LBS_THREADS, sizeof(LbsSmem), s>>>(c->mano, a);
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
@@ -439,7 +481,8 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     bool ok = make_tmap_bf16_2d(&c->tm_patches, c->patches, Mmax, KPATCH, KPATCH, GEMM_BM) &&
               make_tmap_bf16_2d(&c->tm_xn, c->xn, Mmax, DM, DM, GEMM_BM) &&
               make_tmap_bf16_2d(&c->tm_att, c->att, Mmax, DM, DM, GEMM_BM) &&
-              make_tmap_bf16_2d(&c->tm_h, c->hbuf, Mmax, DFF, DFF, GEMM_BM);
+              make_tmap_bf16_2d(&c->tm_h, c->hbuf, Mmax, DFF, DFF, GEMM_BM) &&
+              make_tmap_f32_out(&c->tm_x_out, c->x, Mmax, DM, DM);
     if (!ok) return bail(HM_ERR_CUDA, "activation tensor-map encoding failed");
     if (cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ATT_SMEM_BYTES) != cudaSuccess ||
@@ -459,6 +502,7 @@ void hm_destroy(hm_ctx* c) {
     for (auto& kv : c->w) { cudaFree(kv.second.f32); cudaFree(kv.second.bf16); }
     if (c->crop_host) cudaFreeHost(c->crop_host);
     if (c->crop_event) cudaEventDestroy(c->crop_event);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     delete c;
 }
 
@@ -753,8 +797,35 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
     HM_CUDA(c, cudaMemcpyAsync(c->crop_dev, c->crop_host, (size_t)n * sizeof(CropParams), cudaMemcpyHostToDevice, s));
     HM_CUDA(c, cudaEventRecord(c->crop_event, s));
     c->crop_event_pending = true;
-    crop_warp_normalize_kernel<<<dim3(256, n), 256, 0, s>>>(frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
+    {
+        ProfScope ps(c, s, PC_CROP);
+        crop_warp_normalize_kernel<<<dim3(256, n), 256, 0, s>>>(frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
+    }
     HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
+int hm_profile_enable(hm_ctx* c, int on) {
+    if (!c) return HM_ERR_INVALID;
+    c->prof_on = on != 0;
+    c->prof_used = 0;
+    c->prof_spans.clear();
+    return HM_OK;
+}
+
+int hm_profile_collect(hm_ctx* c, double* ms_per_cat, int32_t* spans_per_cat, int ncat) {
+    if (!c || !ms_per_cat || !spans_per_cat || ncat < PC_COUNT) return fail(c, HM_ERR_INVALID, "hm_profile_collect: need 11 categories");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    HM_CUDA(c, cudaDeviceSynchronize());
+    for (int i = 0; i < ncat; ++i) { ms_per_cat[i] = 0; spans_per_cat[i] = 0; }
+    for (const auto& sp : c->prof_spans) {
+        float ms = 0.f;
+        HM_CUDA(c, cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms_per_cat[sp.cat] += ms;
+        spans_per_cat[sp.cat] += 1;
+    }
+    c->prof_used = 0;
+    c->prof_spans.clear();
     return HM_OK;
 }
 
@@ -810,14 +881,17 @@ int hm_test_gemm(hm_ctx* c, int cta_group, int bn, int epi, int w_format, const 
                  int K, void* stream) {
     if (!c || !A || !W || !bias || !out) return fail(c, HM_ERR_INVALID, "hm_test_gemm: null pointer");
     HM_CUDA(c, cudaSetDevice(c->device));
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tout;
     if (!make_tmap_bf16_2d(&ta, A, M, K, K, GEMM_BM) || !make_tmap_bf16_2d(&tb, W, N, K, K, bn / (cta_group == 1 ? 1 : 2)))
         return fail(c, HM_ERR_CUDA, "hm_test_gemm: tensor map encoding failed");
+    tout = ta;
+    if (epi == EPI_BIAS_RESID_F32 && !make_tmap_f32_out(&tout, out, M, N, N))
+        return fail(c, HM_ERR_CUDA, "hm_test_gemm: output tensor map encoding failed");
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
     p.b_format = w_format ? 1u : 0u;
     GemmPlan plan{cta_group == 1 ? 1 : 2, bn};
-    HM_CUDA(c, gemm_launch(plan, epi, ta, tb, p, c->num_sms, reinterpret_cast<cudaStream_t>(stream)));
+    HM_CUDA(c, gemm_launch(plan, epi, ta, tb, tout, p, c->num_sms, reinterpret_cast<cudaStream_t>(stream)));
     return HM_OK;
 }
 

@@ -130,6 +130,26 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
         : "memory");
 }
 
+// smem tile -> global with an fp32 add performed at L2 (out += tile): the residual stream is never
+// read by the SM.  Bulk-group completion: commit, then wait (.read = smem reusable, plain = done).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src,
+                                                  int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05
 // ----------------------------------------------------------------------------------------------

@@ -177,6 +177,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.hm_forward_launch_count(self.h))
 
+    def profile_enable(self, on=True):
+        self.check(self.lib.hm_profile_enable(self.h, 1 if on else 0))
+
+    def profile_collect(self):
+        """-> {category: (total_ms, spans)} since the last collect (synchronises the device)."""
+        n = len(_lib.PROFILE_CATEGORIES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int32 * n)()
+        self.check(self.lib.hm_profile_collect(self.h, ms, cnt, n))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROFILE_CATEGORIES)}
+
 
 class HAMER:
     """The reference's ``HAMER`` (inference surface).  ``model(batch)`` returns the same two

@@ -119,6 +119,14 @@ int hm_mano_lbs(hm_ctx* ctx, const float* betas, const float* rotmats, const flo
 int hm_forward_launch_count(const hm_ctx* ctx);
 /* Library / build identification string. */
 const char* hm_version(void);
+/* Optional per-category device timing.  While enabled, every kernel launch of the hot path is
+ * bracketed by CUDA events recorded on the launch stream (no synchronisation, a few microseconds
+ * of host time per launch).  hm_profile_collect synchronises the device, returns the summed
+ * elapsed milliseconds and the number of bracketed spans per category, and resets the recorder.
+ * Categories (ncat >= 11): 0 im2col, 1 gemm_patch, 2 layernorm, 3 gemm_qkv, 4 attention,
+ * 5 gemm_proj, 6 gemm_fc1, 7 gemm_fc2, 8 decoder head (one span per call), 9 mano_lbs, 10 crop. */
+int hm_profile_enable(hm_ctx* ctx, int on);
+int hm_profile_collect(hm_ctx* ctx, double* ms_per_cat, int32_t* spans_per_cat, int ncat);
 
 /* ---- test hooks (used by tests/ only; same kernels as the hot path) ----------------------------
  * C[M,N] = A[M,K] * W[N,K]^T with the fused epilogue `epi` (0 bias->fp16, 1 bias+GELU->fp16,

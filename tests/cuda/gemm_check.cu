@@ -100,9 +100,9 @@ int main(int argc, char** argv) {
     ref_gemm<<<dim3((N + 127) / 128, M), 128>>>(dA, dW, w_fmt, dbias, dpos, 192, dres, dref, M, N, K, epi);
     CK(cudaDeviceSynchronize());
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tout;
     if (!make_tmap_bf16_2d(&ta, dA, M, K, K, GEMM_BM) ||
-        !make_tmap_bf16_2d(&tb, dW, N, K, K, bn / cg)) {
+        !make_tmap_bf16_2d(&tb, dW, N, K, K, bn / cg) || !make_tmap_f32_out(&tout, dout_f, M, N, N)) {
         printf("tensor map encode failed\n");
         return 2;
     }
@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
     p.pos_rows = 192;
     p.b_format = (uint32_t)w_fmt;
     GemmPlan plan = {cg, bn};
-    CK(gemm_launch(plan, epi, ta, tb, p, num_sms, 0));
+    CK(gemm_launch(plan, epi, ta, tb, tout, p, num_sms, 0));
     CK(cudaDeviceSynchronize());
 
     // compare
@@ -166,9 +166,9 @@ int main(int argc, char** argv) {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        for (int i = 0; i < 3; ++i) CK(gemm_launch(plan, epi, ta, tb, p, num_sms, 0));
+        for (int i = 0; i < 3; ++i) CK(gemm_launch(plan, epi, ta, tb, tout, p, num_sms, 0));
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < iters; ++i) CK(gemm_launch(plan, epi, ta, tb, p, num_sms, 0));
+        for (int i = 0; i < iters; ++i) CK(gemm_launch(plan, epi, ta, tb, tout, p, num_sms, 0));
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms, e0, e1));
