@@ -86,14 +86,17 @@ struct GemmCfg {
 // of erff(): ~14 issue slots instead of ~25, which is what bounds the fc1 epilogue.
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // 1 ulp, arg in [1, inf)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float e = exp2f(-1.4426950408889634f * z * z);
-    const float erf_abs = fmaf(-poly * t, e, 1.0f);             // erf(|x|/sqrt2)
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));  // exp(-z^2), arg <= 0
+    const float q = poly * t * e;                                // 1 - erf(|x|/sqrt2)  in (0, 1]
+    // 0.5 x (1 + sign(x) (1 - q)) = x - 0.5 x q  for x >= 0,  0.5 x q  for x < 0
+    const float hxq = 0.5f * x * q;
+    return x >= 0.f ? x - hxq : hxq;
 }
 
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -31,6 +32,7 @@ constexpr int KPATCH = 1536;   // 2 x 768: [hi | lo] split of the fp32 pixels
 constexpr int HD = 1024;       // decoder width
 constexpr int HDEPTH = 6;
 constexpr int NREAD = 109;     // 96 pose6d + 10 betas + 3 cam
+constexpr int MANO_CHUNK = 8192;  // hands per MANO pass: 80 MB of fp32 v_posed stays inside the 126 MB L2
 
 std::string g_create_error;
 
@@ -106,6 +108,9 @@ struct hm_ctx {
     // MANO
     ManoDevice mano{};
     std::vector<void*> mano_allocs;
+    __half* m_coef = nullptr;     // [MANO_CHUNK, 320]
+    float *m_vposed = nullptr, *m_A = nullptr, *m_jpos = nullptr;
+    CUtensorMap tm_mcoef, tm_mbasis;
 
     // preprocess
     uint8_t* frame_dev = nullptr;
@@ -382,13 +387,27 @@ int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaS
 
 int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
              float* verts, float* joints, float* kp2d, cudaStream_t s) {
-    LbsArgs a;
-    a.betas = betas; a.rotmats = rotmats; a.cam_t = cam_t; a.verts = verts; a.joints = joints;
-    a.kp2d = (cam_t != nullptr) ? kp2d : nullptr;
-    a.focal_over_size = 5000.0f / 256.0f;
-    a.B = B;
     ProfScope ps(c, s, PC_MANO_LBS);
-    mano_lbs_kernel<<<(B + LBS_HANDS - 1) / LBS_HANDS, LBS_THREADS, sizeof(LbsSmem), s>>>(c->mano, a);
+    for (int lo = 0; lo < B; lo += MANO_CHUNK) {                 // chunk: v_posed stays L2-resident
+        const int n = (B - lo < MANO_CHUNK) ? (B - lo) : MANO_CHUNK;
+        ManoPrepArgs pa;
+        pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
+        pa.coef = c->m_coef; pa.A = c->m_A; pa.jpos = c->m_jpos; pa.B = n;
+        mano_prep_kernel<<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
+        GemmParams p;
+        p.M = n; p.N = MANO_NPAD; p.K = MANO_KTOT; p.bias = c->mano.template_n; p.out = c->m_vposed;
+        p.ldo = MANO_NPAD; p.pos = c->mano.zero_row; p.pos_rows = 1; p.b_format = 0;
+        GemmPlan plan{c->plan.cta_group, 128};
+        HM_CUDA(c, gemm_launch(plan, EPI_BIAS_POS_F32, c->tm_mcoef, c->tm_mbasis, c->tm_mcoef, p, c->num_sms, s));
+        ManoSkinArgs a;
+        a.vposed = c->m_vposed; a.A = c->m_A; a.jpos = c->m_jpos;
+        a.cam_t = cam_t ? cam_t + (size_t)lo * 3 : nullptr;
+        a.verts = verts + (size_t)lo * MANO_V * 3; a.joints = joints + (size_t)lo * 63;
+        a.kp2d = (cam_t != nullptr && kp2d != nullptr) ? kp2d + (size_t)lo * 42 : nullptr;
+        a.focal_over_size = 5000.0f / 256.0f;
+        a.B = n;
+        mano_skin_kernel<<<(n + SKIN_HANDS - 1) / SKIN_HANDS, MANO_VTHREADS, sizeof(SkinSmem), s>>>(c->mano, a);
+    }
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
 }
@@ -486,8 +505,8 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     if (!ok) return bail(HM_ERR_CUDA, "activation tensor-map encoding failed");
     if (cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ATT_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(mano_lbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(LbsSmem)) != cudaSuccess)
+        cudaFuncSetAttribute(mano_skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(SkinSmem)) != cudaSuccess)
         return bail(HM_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
     *out = c;
     return HM_OK;
@@ -698,15 +717,20 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         if (tip_ids[q] < 0 || tip_ids[q] >= MANO_V) return fail(c, HM_ERR_INVALID, "hm_set_mano: tip id out of range");
     for (int q = 0; q < 21; ++q)
         if (joint_map[q] < 0 || joint_map[q] >= 21) return fail(c, HM_ERR_INVALID, "hm_set_mano: joint_map out of range");
-    // basis[k][coord][vertex(800)]
-    std::vector<float> basis((size_t)MANO_K * 3 * MANO_VPAD, 0.f);
+    // GEMM weight: basis16[n = v*3+c][k] with k = [hi(160) | lo(160)], k < 10 shapedirs, 10..144 posedirs
+    std::vector<__half> basis16((size_t)MANO_NPAD * MANO_KTOT, __float2half(0.f));
+    std::vector<float> tmpl(MANO_NPAD, 0.f), zrow(MANO_NPAD, 0.f);
     for (int v = 0; v < MANO_V; ++v)
         for (int cdim = 0; cdim < 3; ++cdim) {
-            basis[(size_t)(0 * 3 + cdim) * MANO_VPAD + v] = v_template[v * 3 + cdim];
-            for (int l = 0; l < 10; ++l)
-                basis[(size_t)((1 + l) * 3 + cdim) * MANO_VPAD + v] = shapedirs[(v * 3 + cdim) * 10 + l];
-            for (int k = 0; k < 135; ++k)
-                basis[(size_t)((11 + k) * 3 + cdim) * MANO_VPAD + v] = posedirs[(size_t)k * 2334 + v * 3 + cdim];
+            const int n = v * 3 + cdim;
+            tmpl[n] = v_template[n];
+            for (int k = 0; k < 145; ++k) {
+                const float b = (k < 10) ? shapedirs[n * 10 + k] : posedirs[(size_t)(k - 10) * 2334 + n];
+                const __half hi = __float2half_rn(b);
+                const __half lo = __float2half_rn(b - __half2float(hi));
+                basis16[(size_t)n * MANO_KTOT + k] = hi;
+                basis16[(size_t)n * MANO_KTOT + MANO_KB + k] = lo;
+            }
         }
     // folded joint regressor (double accumulation; one-time)
     std::vector<float> jt(48), js(480);
@@ -722,20 +746,33 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
                 js[(j * 3 + cdim) * 10 + l] = (float)s;
             }
         }
-    // sparse skinning weights
-    std::vector<int32_t> sidx((size_t)MANO_VPAD * MANO_MAX_NNZ, 0);
-    std::vector<float> sw((size_t)MANO_VPAD * MANO_MAX_NNZ, 0.f);
+    // skinning tables: the kernel walks each warp's union of joints with broadcast shared-memory reads;
+    // lanes whose vertex does not use a joint carry weight 0 for it
+    std::vector<int> order(MANO_V);
+    std::vector<uint32_t> mask(MANO_V, 0);
     for (int v = 0; v < MANO_V; ++v) {
-        int n = 0;
-        for (int j = 0; j < 16; ++j) {
-            const float wv = lbs_weights[v * 16 + j];
-            if (wv != 0.f) {
-                if (n == MANO_MAX_NNZ) return fail(c, HM_ERR_INVALID, "hm_set_mano: more than 8 skinning weights on a vertex");
-                sidx[(size_t)v * MANO_MAX_NNZ + n] = j;
-                sw[(size_t)v * MANO_MAX_NNZ + n] = wv;
-                ++n;
+        order[v] = v;
+        for (int j = 0; j < 16; ++j) if (lbs_weights[v * 16 + j] != 0.f) mask[v] |= 1u << j;
+    }
+    // natural vertex order: a warp's 32 vertices are contiguous in memory (coalesced I/O without staging);
+    // sorting by joint set would shrink the unions (4.4 vs 6.6 joints on MANO) but scatter the stores
+    std::vector<int32_t> perm(MANO_VTHREADS, -1), wnu(MANO_WARPS, 0), wun((size_t)MANO_WARPS * MANO_MAX_UNION, 0);
+    std::vector<float> lw((size_t)MANO_VTHREADS * MANO_MAX_UNION, 0.f);
+    for (int t = 0; t < MANO_V; ++t) perm[t] = order[t];
+    for (int w = 0; w < MANO_WARPS; ++w) {
+        uint32_t um = 0;
+        for (int l = 0; l < 32; ++l) if (perm[w * 32 + l] >= 0) um |= mask[perm[w * 32 + l]];
+        int nu = 0;
+        for (int j = 0; j < 16; ++j)
+            if (um & (1u << j)) {
+                wun[(size_t)w * MANO_MAX_UNION + nu] = j;
+                for (int l = 0; l < 32; ++l) {
+                    const int v = perm[w * 32 + l];
+                    if (v >= 0) lw[(size_t)(w * 32 + l) * MANO_MAX_UNION + nu] = lbs_weights[v * 16 + j];
+                }
+                ++nu;
             }
-        }
+        wnu[w] = nu;
     }
     for (void* p : c->mano_allocs) cudaFree(p);
     c->mano_allocs.clear();
@@ -748,11 +785,28 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         *dst = d;
         return cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
     };
-    HM_CUDA(c, up(basis.data(), basis.size() * 4, reinterpret_cast<const void**>(&c->mano.basis)));
+    HM_CUDA(c, up(basis16.data(), basis16.size() * 2, reinterpret_cast<const void**>(&c->mano.basis16)));
+    HM_CUDA(c, up(tmpl.data(), tmpl.size() * 4, reinterpret_cast<const void**>(&c->mano.template_n)));
+    HM_CUDA(c, up(zrow.data(), zrow.size() * 4, reinterpret_cast<const void**>(&c->mano.zero_row)));
     HM_CUDA(c, up(jt.data(), jt.size() * 4, reinterpret_cast<const void**>(&c->mano.j_template)));
     HM_CUDA(c, up(js.data(), js.size() * 4, reinterpret_cast<const void**>(&c->mano.j_shapedirs)));
-    HM_CUDA(c, up(sidx.data(), sidx.size() * 4, reinterpret_cast<const void**>(&c->mano.skin_idx)));
-    HM_CUDA(c, up(sw.data(), sw.size() * 4, reinterpret_cast<const void**>(&c->mano.skin_w)));
+    HM_CUDA(c, up(perm.data(), perm.size() * 4, reinterpret_cast<const void**>(&c->mano.perm)));
+    HM_CUDA(c, up(wnu.data(), wnu.size() * 4, reinterpret_cast<const void**>(&c->mano.warp_nu)));
+    HM_CUDA(c, up(wun.data(), wun.size() * 4, reinterpret_cast<const void**>(&c->mano.warp_union)));
+    HM_CUDA(c, up(lw.data(), lw.size() * 4, reinterpret_cast<const void**>(&c->mano.lane_w)));
+    // per-chunk workspace (coefficients, v_posed, skinning transforms, posed joints) + tensor maps
+    {
+        void* d = nullptr;
+        const size_t ch = MANO_CHUNK;
+        HM_CUDA(c, cudaMalloc(&d, ch * MANO_KTOT * 2)); c->mano_allocs.push_back(d); c->m_coef = reinterpret_cast<__half*>(d);
+        HM_CUDA(c, cudaMalloc(&d, ch * MANO_NPAD * 4)); c->mano_allocs.push_back(d); c->m_vposed = reinterpret_cast<float*>(d);
+        HM_CUDA(c, cudaMalloc(&d, ch * MANO_J * 12 * 4)); c->mano_allocs.push_back(d); c->m_A = reinterpret_cast<float*>(d);
+        HM_CUDA(c, cudaMalloc(&d, ch * MANO_J * 3 * 4)); c->mano_allocs.push_back(d); c->m_jpos = reinterpret_cast<float*>(d);
+        HM_CUDA(c, cudaMemset(c->m_coef, 0, ch * MANO_KTOT * 2));
+        if (!make_tmap_bf16_2d(&c->tm_mcoef, c->m_coef, ch, MANO_KTOT, MANO_KTOT, GEMM_BM) ||
+            !make_tmap_bf16_2d(&c->tm_mbasis, c->mano.basis16, MANO_NPAD, MANO_KTOT, MANO_KTOT, 128 / c->plan.cta_group))
+            return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed");
+    }
     for (int j = 0; j < 16; ++j) c->mano.parents[j] = parents[j];
     for (int q = 0; q < 5; ++q) c->mano.tip_ids[q] = tip_ids[q];
     for (int q = 0; q < 21; ++q) c->mano.joint_map[q] = joint_map[q];
@@ -871,8 +925,8 @@ int hm_forward(hm_ctx* c, const float* img, int B, const hm_outputs* out, void* 
 
 int hm_forward_launch_count(const hm_ctx*) {
     // im2col + patch GEMM + 32 x (LN, qkv, attention, proj, LN, fc1, fc2) + last LN
-    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO
-    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + 1;
+    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO (prep, blend GEMM, skinning)
+    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + 3;
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------

@@ -127,7 +127,7 @@ def synthetic_mano(seed=0):
     order = np.argsort(-w, axis=1)
     mask = np.zeros_like(w, dtype=bool)
     np.put_along_axis(mask, order[:, :6], True, axis=1)
-    w = np.where(mask & (w > 1e-4 * w.max(axis=1, keepdims=True)), w, 0.0)
+    w = np.where(mask & (w > 0.02 * w.max(axis=1, keepdims=True)), w, 0.0)   # mean ~2.6 non-zeros like MANO
     w /= w.sum(axis=1, keepdims=True)
     # fingertip vertices are rigidly attached to the distal joints (as in MANO)
     for tip, joint in zip(TIP_IDS, (15, 3, 6, 12, 9)):

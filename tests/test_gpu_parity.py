@@ -182,8 +182,8 @@ def test_mano_lbs_vs_oracle(engine, oracle_model, B):
     verts, joints, kp2d = engine.mano_lbs(betas.to(dev), rot.to(dev), cam_t.to(dev))
     v_ref, j_ref = mano_forward(rot[:, :1], rot[:, 1:], betas, oracle_model.mano_data)
     k_ref = perspective_projection(j_ref, cam_t, torch.full((B, 2), 5000.0 / 256))
-    assert (verts.cpu() - v_ref).norm(dim=-1).max().item() < 0.005 * MM        # 0.005 mm
-    assert (joints.cpu() - j_ref).norm(dim=-1).max().item() < 0.005 * MM
+    assert (verts.cpu() - v_ref).norm(dim=-1).max().item() < 0.02 * MM         # 0.02 mm (fp16 blend coefficients)
+    assert (joints.cpu() - j_ref).norm(dim=-1).max().item() < 0.02 * MM
     assert (kp2d.cpu() - k_ref).abs().max().item() * 256 < 0.01                # px
 
 
