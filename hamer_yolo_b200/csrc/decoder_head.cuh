@@ -20,10 +20,11 @@
 namespace hm {
 
 // ------------------------------------------------------------------------------------------------
-// Y[b, n] (+)= act( sum_k X[b, k] * W[n, k] + bias[n] ),  b < B, n < N, K % 128 == 0 or K == 64.
+// Y[b, n] (+)= act( scale * sum_k X[b, k] * W[n, k] + bias[n] ),  b < B, n < N, K % 64 == 0, K <= 1280.
 // Batched over blockIdx.z with element strides (per-head products of the cross-attention).
-// One warp per output column n: the W row lives in registers, X rows stream from shared memory
-// (a 64-row x K tile staged per block), 8 columns per block.
+// Block = 8 warps = 8 output columns x a tile of 16 rows (crops): the whole [16 x K] X tile is staged
+// once in shared memory (cp.async), each warp keeps its W row in registers (K/32 floats per lane),
+// so there is one global round trip and one barrier per block; 64 KB of smem lets 3 blocks share an SM.
 // ------------------------------------------------------------------------------------------------
 enum SkinnyEpi : int { SK_NONE = 0, SK_GELU = 1, SK_RESID = 2 };
 
@@ -36,15 +37,20 @@ struct SkinnyParams {
     float scale;                         // applied to the dot product before bias
 };
 
-constexpr int SK_ROWS = 64;   // crops per block tile
-constexpr int SK_COLS = 8;    // output columns (warps) per block
-constexpr int SK_KC = 128;    // K chunk staged in smem
+constexpr int SK_ROWS = 16;     // crops per block tile
+constexpr int SK_COLS = 8;      // output columns (warps) per block
+constexpr int SK_KMAX = 1280;   // largest K (cross-attention value projection)
 
-// Reduce 32 per-lane partial sums for 32 rows at once: afterwards lane i holds the full sum of row i
-// (31 shuffles instead of 32 x 5).
-__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+__device__ __forceinline__ void sk_cp_async16(float* smem_dst, const float* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(g) : "memory");
+}
+
+// Reduce 16 per-lane partial sums for 16 rows at once: afterwards lanes i and i + 16 hold the full sum
+// of row i (15 + 1 shuffles instead of 16 x 5).
+__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
+    for (int o = 8; o >= 1; o >>= 1) {
         const bool up = (lane & o) != 0;
 #pragma unroll
         for (int j = 0; j < o; ++j) {
@@ -53,13 +59,13 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
             v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
     }
-    return v[0];
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(SK_COLS * 32)
 skinny_linear_kernel(const SkinnyParams p) {
-    __shared__ __align__(16) float xs[SK_ROWS][SK_KC];
+    extern __shared__ __align__(16) float sk_xs[];              // [SK_ROWS][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * SK_COLS + warp;
     const int b0 = blockIdx.y * SK_ROWS;
@@ -69,68 +75,53 @@ skinny_linear_kernel(const SkinnyParams p) {
     float* Y = p.Y + z * p.y_bs;
     const int rows = min(SK_ROWS, p.B - b0);
     const bool active = n < p.N;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = p.K, K4 = K >> 2;
+
+    // X tile -> smem (rows >= rows are zero-filled so the inner loop has no predicates)
+    for (int e = threadIdx.x; e < SK_ROWS * K4; e += blockDim.x) {
+        const int r = e / K4, c = e - r * K4;
+        float* dst = sk_xs + (size_t)r * K + c * 4;
+        if (r < rows) sk_cp_async16(dst, X + (size_t)(b0 + r) * p.ldx + c * 4);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // this warp's W row: lane holds float4 chunks lane, lane + 32, ... (K / 128 of them, <= 10)
+    float4 w[SK_KMAX / 128];
+#pragma unroll
+    for (int i = 0; i < SK_KMAX / 128; ++i) {
+        const int c = lane + 32 * i;
+        w[i] = (active && c < K4) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K) + c)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 
     float acc[SK_ROWS];
 #pragma unroll
-    for (int i = 0; i < SK_ROWS; ++i) acc[i] = 0.f;
-
-    // software pipeline: the next chunk's X tile (8 float4 per thread) and W slice are in flight
-    // while the current chunk is multiplied out of shared memory.  Tile rows >= rows and columns
-    // >= the chunk width are zero-filled so the inner loop has no predicates.
-    float4 xr[SK_ROWS / 8];
-    float4 wn;
-    auto fetch = [&](int k0) {
-        const int kc4 = min(SK_KC, p.K - k0) >> 2;
+    for (int r = 0; r < SK_ROWS; ++r) acc[r] = 0.f;
 #pragma unroll
-        for (int i = 0; i < SK_ROWS / 8; ++i) {
-            const int r = warp + 8 * i;
-            xr[i] = (lane < kc4 && r < rows)
-                        ? *reinterpret_cast<const float4*>(X + (size_t)(b0 + r) * p.ldx + k0 + lane * 4)
-                        : zero4;
-        }
-        wn = (active && lane < kc4)
-                 ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * p.K + k0) + lane) : zero4;
-    };
-    fetch(0);
-    for (int k0 = 0; k0 < p.K; k0 += SK_KC) {
-        __syncthreads();
+    for (int i = 0; i < SK_KMAX / 128; ++i) {
+        const int c = lane + 32 * i;
+        if (i * 32 < K4) {                                      // block-uniform
+            const int cc = c < K4 ? c : 0;                      // lanes past a 64-wide tail re-read chunk 0 (w = 0)
 #pragma unroll
-        for (int i = 0; i < SK_ROWS / 8; ++i)
-            reinterpret_cast<float4*>(&xs[warp + 8 * i][0])[lane] = xr[i];
-        const float4 w = wn;
-        __syncthreads();
-        if (k0 + SK_KC < p.K) fetch(k0 + SK_KC);
-#pragma unroll
-        for (int r = 0; r < SK_ROWS; ++r) {
-            const float4 x = reinterpret_cast<const float4*>(&xs[r][0])[lane];
-            acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+            for (int r = 0; r < SK_ROWS; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(sk_xs + (size_t)r * K + cc * 4);
+                acc[r] = fmaf(x.x, w[i].x, fmaf(x.y, w[i].y, fmaf(x.z, w[i].z, fmaf(x.w, w[i].w, acc[r]))));
+            }
         }
     }
-    // lane i ends up with the dot products of rows i and i + 32
-    float lo[32], hi[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { lo[i] = acc[i]; hi[i] = acc[i + 32]; }
-    float v0 = warp_transpose_reduce32(lo, lane);
-    float v1 = warp_transpose_reduce32(hi, lane);
+    float v = warp_transpose_reduce16(acc, lane);               // lanes i, i+16: row i
     if (!active) return;
-    const float bias = p.bias ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
-    v0 = v0 * p.scale + bias;
-    v1 = v1 * p.scale + bias;
-    if constexpr (EPI == SK_GELU) {
-        v0 = 0.5f * v0 * (1.0f + erff(v0 * 0.70710678118654752440f));
-        v1 = 0.5f * v1 * (1.0f + erff(v1 * 0.70710678118654752440f));
+    const int r = lane & 15;
+    if (lane < 16 && r < rows) {
+        const float bias = p.bias ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
+        v = v * p.scale + bias;
+        if constexpr (EPI == SK_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        float* y = Y + (size_t)(b0 + r) * p.ldy + n;
+        if constexpr (EPI == SK_RESID) v += *y;
+        *y = v;
     }
-    float* y0 = Y + (size_t)(b0 + lane) * p.ldy + n;
-    float* y1 = Y + (size_t)(b0 + lane + 32) * p.ldy + n;
-    const bool ok0 = lane < rows, ok1 = lane + 32 < rows;
-    if constexpr (EPI == SK_RESID) {
-        const float r0 = ok0 ? *y0 : 0.f, r1 = ok1 ? *y1 : 0.f;     // both loads in flight together
-        v0 += r0;
-        v1 += r1;
-    }
-    if (ok0) *y0 = v0;
-    if (ok1) *y1 = v1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -99,6 +99,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x >= 0.f ? x - hxq : hxq;
 }
 
+// Two elements per instruction with the packed fp32 pipe of sm_100 (FFMA2 / FMUL2): the fc1 epilogue
+// is issue-bound, so halving the FMA/MUL count of the polynomial is what matters (MUFU stays scalar).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+    const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+    float2 t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+    float2 poly = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    poly = __ffma2_rn(poly, t, make_float2(1.421413741f, 1.421413741f));
+    poly = __ffma2_rn(poly, t, make_float2(-0.284496736f, -0.284496736f));
+    poly = __ffma2_rn(poly, t, make_float2(0.254829592f, 0.254829592f));
+    const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+    const float2 q = __fmul2_rn(__fmul2_rn(poly, t), e);
+    const float2 hxq = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), q);
+    return make_float2(x.x >= 0.f ? x.x - hxq.x : hxq.x, x.y >= 0.f ? x.y - hxq.y : hxq.y);
+}
+
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -271,7 +291,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             }
                             if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                                for (int e = 0; e < 8; e += 2) {
+                                    const float2 g = gelu_erf2(make_float2(v[e], v[e + 1]));
+                                    v[e] = g.x; v[e + 1] = g.y;
+                                }
                             }
                             uint4 o;
                             o.x = pack_act2(v[0], v[1]);

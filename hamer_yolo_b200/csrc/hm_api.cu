@@ -294,10 +294,12 @@ cudaError_t launch_skinny(int epi, const float* X, int ldx, long long x_bs, cons
     SkinnyParams p;
     p.X = X; p.ldx = ldx; p.x_bs = x_bs; p.W = W; p.w_bs = w_bs; p.bias = bias; p.bias_bs = bias_bs;
     p.Y = Y; p.ldy = ldy; p.y_bs = y_bs; p.B = B; p.N = N; p.K = K; p.scale = scale;
+    if (K % 64 != 0 || K > SK_KMAX || ldx % 4 != 0) return cudaErrorInvalidValue;
     dim3 grid((N + SK_COLS - 1) / SK_COLS, (B + SK_ROWS - 1) / SK_ROWS, batch);
-    if (epi == SK_NONE) skinny_linear_kernel<SK_NONE><<<grid, SK_COLS * 32, 0, s>>>(p);
-    else if (epi == SK_GELU) skinny_linear_kernel<SK_GELU><<<grid, SK_COLS * 32, 0, s>>>(p);
-    else skinny_linear_kernel<SK_RESID><<<grid, SK_COLS * 32, 0, s>>>(p);
+    const size_t smem = (size_t)SK_ROWS * K * sizeof(float);
+    if (epi == SK_NONE) skinny_linear_kernel<SK_NONE><<<grid, SK_COLS * 32, smem, s>>>(p);
+    else if (epi == SK_GELU) skinny_linear_kernel<SK_GELU><<<grid, SK_COLS * 32, smem, s>>>(p);
+    else skinny_linear_kernel<SK_RESID><<<grid, SK_COLS * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -503,7 +505,11 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
               make_tmap_bf16_2d(&c->tm_h, c->hbuf, Mmax, DFF, DFF, GEMM_BM) &&
               make_tmap_f32_out(&c->tm_x_out, c->x, Mmax, DM, DM);
     if (!ok) return bail(HM_ERR_CUDA, "activation tensor-map encoding failed");
-    if (cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const int sk_smem = SK_ROWS * SK_KMAX * (int)sizeof(float);
+    if (cudaFuncSetAttribute(skinny_linear_kernel<SK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(skinny_linear_kernel<SK_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(skinny_linear_kernel<SK_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ATT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(mano_skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(SkinSmem)) != cudaSuccess)
