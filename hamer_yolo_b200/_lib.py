@@ -13,7 +13,7 @@ c_float_p = C.POINTER(C.c_float)
 
 class HmConfig(C.Structure):
     _fields_ = [('max_batch', C.c_int32), ('max_frame_bytes', C.c_int32),
-                ('gemm_cta_group', C.c_int32), ('reserved', C.c_int32 * 5)]
+                ('gemm_cta_group', C.c_int32), ('attention_legacy', C.c_int32), ('reserved', C.c_int32 * 4)]
 
 
 class HmOutputs(C.Structure):
@@ -70,7 +70,7 @@ def load():
     lib.hm_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32), i32]
     lib.hm_test_gemm.argtypes =[vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.hm_test_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, i32, vp]
-    lib.hm_test_attention.argtypes = [vp, vp, vp, i32, vp]
+    lib.hm_test_attention.argtypes = [vp, i32, vp, vp, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ('hm_destroy', 'hm_last_error', 'hm_version'):

@@ -1,0 +1,222 @@
+// Multi-head self-attention core on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces Attention.forward lines vit.py:112-122 of the reference (q*scale, q@k^T, softmax, @v).
+//
+// One CTA = one (crop, head): grid (16, B), 256 threads, two CTAs per SM.
+//   1. Q, K, V (192 x 80 fp16 each) arrive by six TMA copies.  head_dim 80 = 64 + 16, so every matrix is
+//      staged as a 128B-swizzled tile (d 0..63, 128-byte rows) plus a 32B-swizzled tile (d 64..79):
+//      Q and K are K-major UMMA operands, V (stored [token][d]) is an MN-major operand.
+//      (Measured alternatives: cp.async.16 into un-swizzled core matrices is issue-bound at ~10k cycles
+//      per tile, LDG/STS the same, TMA with a 16-byte inner box ~7k; this version ~4.8k, mostly latency.)
+//   2. the 192 queries are processed as two UMMA M = 128 blocks (rows 0..127, then 128..191 whose upper
+//      64 TMEM lanes idle) that share the K / V tiles and the TMEM columns:
+//        S = Q K^T : 5 x tcgen05.mma (N 192, K 16), fp32 accumulator in TMEM columns [0,192)
+//        softmax   : thread = (row = TMEM lane, half of the columns); tcgen05.ld, row max and row sum
+//                    in fp32 (the two halves of a row meet through shared memory), exp2 via ex2.approx;
+//                    the fp16 probabilities overwrite S in place (tcgen05.st, columns [0,96))
+//        O = P V   : 12 x 2 tcgen05.mma with the A operand read from TMEM (N 64 + N 16, K 16),
+//                    accumulator in the already consumed S columns [96,176)
+//        O / rowsum -> fp16 -> global
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace hm {
+
+constexpr int AT5_T = 192;
+constexpr int AT5_D = 80;
+constexpr int AT5_THREADS = 256;                    // 8 warps: TMEM lane quadrant = warp % 4, column half = warp / 4
+constexpr uint32_t AT5_TA = AT5_T * 128;            // bytes of a 64-column (128-byte rows) tile
+constexpr uint32_t AT5_TB = AT5_T * 32;             // bytes of a 16-column (32-byte rows) tile
+constexpr uint32_t AT5_DATA = 3 * AT5_TA + 3 * AT5_TB;                  // [Qa | Ka | Va | Qb | Kb | Vb]
+constexpr uint32_t AT5_SMEM_BYTES = AT5_DATA + 1024 /*align*/ + 64 /*barriers*/ + 2 * 128 * 4 /*row exchange*/;
+constexpr uint32_t AT5_TMEM_COLS = 256;
+
+// TIMING (test hook only): thread 0 of every CTA records the clock at each phase boundary into dbg.
+template <bool TIMING>
+__global__ void __launch_bounds__(AT5_THREADS, 2)
+vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm32,
+                         __half* __restrict__ out, float scale_log2e, long long* __restrict__ dbg) {
+    long long tk[16];
+    int nt = 0;
+    auto tick = [&]() { if constexpr (TIMING) { if (threadIdx.x == 0) tk[nt++] = clock64(); } };
+    tick();
+    extern __shared__ uint8_t at5_smem_raw[];
+    const uint32_t raw = ptx::smem_u32(at5_smem_raw);
+    uint8_t* smem = at5_smem_raw + ((1024u - (raw & 1023u)) & 1023u);    // 128B-swizzled tiles: 1 KB aligned
+    const uint32_t sbase = ptx::smem_u32(smem);
+    const uint32_t sQ = sbase, sK = sbase + AT5_TA, sV = sbase + 2 * AT5_TA;
+    const uint32_t sQb = sbase + 3 * AT5_TA, sKb = sQb + AT5_TB, sVb = sKb + AT5_TB;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AT5_DATA);        // [0] S done, [1] O done, [2] loads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+    float* xch = reinterpret_cast<float*>(bar + 4);                      // [2][128] row max / row sum exchange
+
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, half = warp >> 2;                         // TMEM lane quadrant, column half
+
+    // ---- 1. loads ----------------------------------------------------------------------------------------
+    if (tid == 0) {
+        ptx::mbar_init(&bar[0], 1);
+        ptx::mbar_init(&bar[1], 1);
+        ptx::mbar_init(&bar[2], 1);
+        ptx::fence_mbar_init();
+        ptx::prefetch_tmap(&tm128);
+        ptx::prefetch_tmap(&tm32);
+        ptx::mbar_arrive_expect_tx(&bar[2], AT5_DATA);
+        const int row0 = b * AT5_T, col = h * AT5_D;
+        for (int m = 0; m < 3; ++m) {                                    // Q, K, V column blocks of qkv
+            ptx::tma_load_2d(smem + m * AT5_TA, &tm128, &bar[2], m * 1280 + col, row0);
+            ptx::tma_load_2d(smem + 3 * AT5_TA + m * AT5_TB, &tm32, &bar[2], m * 1280 + col + 64, row0);
+        }
+    }
+    if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, AT5_TMEM_COLS);
+    tick();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    ptx::mbar_wait(&bar[2], 0);
+    tick();
+
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int mblk = 0; mblk < 2; ++mblk) {
+        const int q0 = mblk * 128;
+        const int q_rows = (mblk == 0) ? 128 : (AT5_T - 128);            // valid query rows of this block
+        const uint32_t par = (uint32_t)mblk;                             // mbarrier phase parity of this pass
+        // ---- 2. S = Q K^T (block 1's descriptors start 128 rows further down; its rows 64..127 are
+        //         don't-care data read from the neighbouring tile) ---------------------------------------
+        if (tid == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16kind_f32(0, 0, 128, AT5_T);
+#pragma unroll
+            for (int ks = 0; ks < AT5_D / 16; ++ks) {
+                uint64_t da, db;
+                if (ks < 4) {        // d 0..63: 128B-swizzled tiles, 32 bytes per K step inside the atom
+                    da = ptx::make_smem_desc_k_sw128(sQ + q0 * 128) + (uint64_t)(ks * 2);
+                    db = ptx::make_smem_desc_k_sw128(sK) + (uint64_t)(ks * 2);
+                } else {             // d 64..79: 32B-swizzled tiles (8-row groups 256 bytes apart)
+                    da = ptx::make_smem_desc_swz(sQb + q0 * 32, 16, 256, 6);
+                    db = ptx::make_smem_desc_swz(sKb, 16, 256, 6);
+                }
+                ptx::mma_f16<1>(tmem, da, db, idesc, (uint32_t)(ks != 0));
+            }
+            ptx::mma_commit_1sm(&bar[0]);
+        }
+        ptx::mbar_wait(&bar[0], par);
+        ptx::tc_fence_after();
+        tick();
+
+        // ---- 3. softmax ----------------------------------------------------------------------------------
+        const bool row_live = (quad * 32) < q_rows;                      // warp-uniform
+        float mx = -INFINITY;
+        if (row_live) {
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(lane_addr + half * 96 + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+            }
+            xch[half * 128 + row] = mx;
+        }
+        __syncthreads();
+        uint32_t pk[48];
+        float sum = 0.f;
+        if (row_live) {
+            mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);
+            const float mo = mx * scale_log2e;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(lane_addr + half * 96 + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float p0, p1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(r[2 * j]), scale_log2e, -mo)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2e, -mo)));
+                    sum += p0 + p1;
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    pk[c * 16 + j] = *reinterpret_cast<const uint32_t*>(&hp);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+        __syncthreads();                                                 // every S column has been read
+        ptx::tc_fence_after();
+        if (row_live) {
+            xch[half * 128 + row] = sum;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t q16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) q16[j] = pk[c * 16 + j];
+                ptx::tmem_st_32x16(lane_addr + half * 48 + c * 16, q16); // P (fp16 pairs) over S columns [0,96)
+            }
+            ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        tick();
+
+        // ---- 4. O = P V (A from TMEM; V MN-major: 8-token groups 1024 B / 256 B apart) ---------------------
+        if (tid == 0) {
+            ptx::tc_fence_after();
+            constexpr uint32_t idesc64 = ptx::make_idesc_f16kind_f32(0, 0, 128, 64, 0, 1);
+            constexpr uint32_t idesc16 = ptx::make_idesc_f16kind_f32(0, 0, 128, 16, 0, 1);
+#pragma unroll
+            for (int kk = 0; kk < AT5_T / 16; ++kk) {
+                const uint64_t d64 = ptx::make_smem_desc_swz(sV + kk * 2048, 16, 1024, 2);
+                const uint64_t d16 = ptx::make_smem_desc_swz(sVb + kk * 512, 16, 256, 6);
+                ptx::mma_f16_ts(tmem + 96, tmem + kk * 8, d64, idesc64, (uint32_t)(kk != 0));
+                ptx::mma_f16_ts(tmem + 96 + 64, tmem + kk * 8, d16, idesc16, (uint32_t)(kk != 0));
+            }
+            ptx::mma_commit_1sm(&bar[1]);
+        }
+        ptx::mbar_wait(&bar[1], par);
+        ptx::tc_fence_after();
+        tick();
+
+        // ---- 5. normalise and store: half 0 -> d 0..47, half 1 -> d 48..79 ---------------------------------
+        if (row_live && row < q_rows) {
+            const float inv = 1.0f / (xch[row] + xch[128 + row]);
+            __half* orow = out + ((size_t)b * AT5_T + q0 + row) * 1280 + h * AT5_D + half * 48;
+            const int nchunk = half ? 2 : 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c < nchunk) {
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x16(lane_addr + 96 + half * 48 + c * 16, r);
+                    ptx::tmem_ld_wait();
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __half2 hv = __floats2half2_rn(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&hv);
+                    }
+                    *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        ptx::tc_fence_after();
+        tick();
+    }
+    if constexpr (TIMING) {
+        if (tid == 0) {
+            const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+            for (int i = 0; i < 16; ++i) dbg[(size_t)cta * 16 + i] = i < nt ? tk[i] : 0;
+        }
+    }
+    if (warp == 1) ptx::tmem_dealloc<1>(tmem, AT5_TMEM_COLS);
+}
+
+}  // namespace hm

@@ -58,6 +58,23 @@ inline bool make_tmap_f32_out(CUtensorMap* out, const void* base, uint64_t rows,
     return r == CUDA_SUCCESS;
 }
 
+// 2-D maps over the fp16 qkv buffer [rows, 3840] for the attention kernel: a 64-column box with the
+// 128-byte swizzle and a 16-column box with the 32-byte swizzle (head_dim 80 = 64 + 16), 192 rows each.
+inline bool make_tmap_attn(CUtensorMap* t128, CUtensorMap* t32, const void* base, uint64_t rows) {
+    PFN_tmapEncodeTiled enc = get_tmap_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {3840, rows};
+    cuuint64_t gstride[1] = {3840 * 2};
+    cuuint32_t estr[2] = {1, 1};
+    cuuint32_t b128[2] = {64, 192}, b32[2] = {16, 192};
+    return enc(t128, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, b128, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+           enc(t32, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, b32, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct GemmPlan {
     int cta_group;  // 1 or 2
     int bn;         // 128 or 256

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_tc5.cuh"
 #include "crop_warp.cuh"
 #include "decoder_head.cuh"
 #include "elementwise.cuh"
@@ -97,9 +98,11 @@ struct hm_ctx {
     // workspace (max_batch)
     __half *patches = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;  // fp16 activations
     uint32_t b_format = 0;   // operand format of the backbone GEMMs (A and B): 0 = fp16, 1 = bf16
+    bool att_legacy = false; // true: mma.sync attention kernel instead of the tcgen05 one
     float *x = nullptr, *feats = nullptr;
     CUtensorMap tm_patches, tm_xn, tm_att, tm_h;
     CUtensorMap tm_x_out;   // fp32 residual stream as the target of the TMA reduce-add epilogue
+    CUtensorMap tm_att128, tm_att32;   // qkv buffer: 64- and 16-column boxes for the attention kernel
     // decoder workspace
     float *hx = nullptr, *hy = nullptr, *hv = nullptr, *hq = nullptr, *hu = nullptr, *hsc = nullptr,
           *hpool = nullptr, *ho = nullptr, *hh = nullptr, *hraw = nullptr, *hrot = nullptr,
@@ -325,7 +328,9 @@ int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStre
         { ProfScope ps(c, s, PC_GEMM_QKV);
           if ((rc = run_gemm(c, EPI_BIAS_BF16, c->tm_xn, w.tm_qkv, M, 3 * DM, DM, w.b_qkv, c->qkv, nullptr, s))) return rc; }
         { ProfScope ps(c, s, PC_ATTENTION);
-          vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(c->qkv, c->att, att_scale); }
+          if (c->att_legacy) vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(c->qkv, c->att, att_scale);
+          else vit_attention_tc5_kernel<false><<<dim3(16, B), AT5_THREADS, AT5_SMEM_BYTES, s>>>(
+                   c->tm_att128, c->tm_att32, c->att, att_scale, nullptr); }
         { ProfScope ps(c, s, PC_GEMM_PROJ);
           if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_att, w.tm_proj, M, DM, DM, w.b_proj, c->x, nullptr, s))) return rc; }
         { ProfScope ps(c, s, PC_LAYERNORM); launch_ln<10, __half>(c->x, w.ln2_g, w.ln2_b, c->xn, M, 1e-6f, s); }
@@ -452,6 +457,7 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     c->plan.cta_group = (cfg->gemm_cta_group == 1) ? 1 : 2;
     c->plan.bn = 256;
     c->b_format = 0u;   // fp16 weight operands (kind::f16 requires A and B of the same 16-bit type)
+    c->att_legacy = cfg->attention_legacy != 0;
     if (!get_tmap_encode()) return bail(HM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
     const size_t Mmax = (size_t)cfg->max_batch * TOK, Bm = (size_t)cfg->max_batch;
@@ -503,7 +509,8 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
               make_tmap_bf16_2d(&c->tm_xn, c->xn, Mmax, DM, DM, GEMM_BM) &&
               make_tmap_bf16_2d(&c->tm_att, c->att, Mmax, DM, DM, GEMM_BM) &&
               make_tmap_bf16_2d(&c->tm_h, c->hbuf, Mmax, DFF, DFF, GEMM_BM) &&
-              make_tmap_f32_out(&c->tm_x_out, c->x, Mmax, DM, DM);
+              make_tmap_f32_out(&c->tm_x_out, c->x, Mmax, DM, DM) &&
+              make_tmap_attn(&c->tm_att128, &c->tm_att32, c->qkv, Mmax);
     if (!ok) return bail(HM_ERR_CUDA, "activation tensor-map encoding failed");
     const int sk_smem = SK_ROWS * SK_KMAX * (int)sizeof(float);
     if (cudaFuncSetAttribute(skinny_linear_kernel<SK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
@@ -511,6 +518,10 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
         cudaFuncSetAttribute(skinny_linear_kernel<SK_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
         cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ATT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(vit_attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)AT5_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(vit_attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)AT5_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(mano_skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(SkinSmem)) != cudaSuccess)
         return bail(HM_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
@@ -966,12 +977,27 @@ int hm_test_layernorm(hm_ctx* c, const float* x, const float* gamma, const float
     return HM_OK;
 }
 
-int hm_test_attention(hm_ctx* c, const uint16_t* qkv, uint16_t* out, int B, void* stream) {
+int hm_test_attention(hm_ctx* c, int variant, const uint16_t* qkv, uint16_t* out, int B, void* stream) {
     if (!c || !qkv || !out || B <= 0) return fail(c, HM_ERR_INVALID, "hm_test_attention: bad arguments");
     HM_CUDA(c, cudaSetDevice(c->device));
-    vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out),
-        0.11180339887498948f * 1.4426950408889634f);
+    const float sc = 0.11180339887498948f * 1.4426950408889634f;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (variant == 0)
+        vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(
+            reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), sc);
+    else {   // 1: tcgen05 kernel, 2: same + phase clocks of every CTA (16 x int64 each) copied into `out`
+        CUtensorMap t128, t32;
+        if (!make_tmap_attn(&t128, &t32, qkv, (uint64_t)B * AT5_T))
+            return fail(c, HM_ERR_CUDA, "hm_test_attention: tensor map encoding failed");
+        __half* o = reinterpret_cast<__half*>(out);
+        if (variant == 1)
+            vit_attention_tc5_kernel<false><<<dim3(16, B), AT5_THREADS, AT5_SMEM_BYTES, s>>>(t128, t32, o, sc, nullptr);
+        else {
+            long long* dbg = reinterpret_cast<long long*>(c->hbuf);
+            vit_attention_tc5_kernel<true><<<dim3(16, B), AT5_THREADS, AT5_SMEM_BYTES, s>>>(t128, t32, o, sc, dbg);
+            HM_CUDA(c, cudaMemcpyAsync(out, c->hbuf, (size_t)16 * B * 16 * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+        }
+    }
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
 }

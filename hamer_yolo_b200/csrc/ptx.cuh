@@ -117,6 +117,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // 2-CTA variant: both CTAs of the pair issue it; the transaction bytes land on the barrier of the
 // leader CTA (peer bit cleared in the barrier address).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map,
@@ -239,6 +258,58 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// registers -> TMEM: thread i of the warp writes 16 consecutive 32-bit columns of lane (base + i)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+          "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+          "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (e.g. softmax probabilities) is read from
+// tensor memory (lane = row, two 16-bit K elements per 32-bit column), single CTA.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor without swizzle ("interleaved" canonical layout): 8 x 16-byte core
+// matrices (128 contiguous bytes each); lbo / sbo = byte strides between core matrices.
+//   K-major operand : lbo = next core matrix along K,  sbo = next 8-row group along M/N
+//   MN-major operand: lbo = next 8-row group along K,  sbo = next 8-element group along M/N
+__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (sm_100)
+    return d;                                                     // layout type 0 = no swizzle
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -260,12 +331,28 @@ __device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Generic swizzled descriptor: layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t make_smem_desc_swz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo,
+                                                      uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout & 7u) << 61;
+    return d;
+}
+
 // Instruction descriptor, kind::f16: A, B K-major, D = f32, shape M x N x 16.
 // a_fmt / b_fmt: 0 = f16, 1 = bf16 (independent fields: the activations are fp16, the weights bf16).
-__host__ __device__ constexpr uint32_t make_idesc_f16kind_f32(int a_fmt, int b_fmt, int M, int N) {
+// a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
+__host__ __device__ constexpr uint32_t make_idesc_f16kind_f32(int a_fmt, int b_fmt, int M, int N,
+                                                              int a_mn = 0, int b_mn = 0) {
     return (1u << 4)                       // D format f32
            | (static_cast<uint32_t>(a_fmt) << 7)
            | (static_cast<uint32_t>(b_fmt) << 10)
+           | (static_cast<uint32_t>(a_mn) << 15)
+           | (static_cast<uint32_t>(b_mn) << 16)
            | (static_cast<uint32_t>(N >> 3) << 17)
            | (static_cast<uint32_t>(M >> 4) << 24);
 }

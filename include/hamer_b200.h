@@ -40,7 +40,8 @@ typedef struct hm_config {
     int32_t max_batch;        /* largest B of hm_forward / n of hm_preprocess */
     int32_t max_frame_bytes;  /* largest H*row_stride accepted by hm_preprocess (host frames) */
     int32_t gemm_cta_group;   /* 0 = default (2: CTA-pair UMMA M=256), 1 = single-CTA tiles */
-    int32_t reserved[5];
+    int32_t attention_legacy; /* 0 = tcgen05/TMEM attention kernel (default), 1 = mma.sync kernel */
+    int32_t reserved[4];
 } hm_config;
 
 /* Device pointers of the tensors HAMER.forward_step returns (hamer/hamer/models/hamer.py:124-156).
@@ -139,8 +140,10 @@ int hm_test_gemm(hm_ctx* ctx, int cta_group, int bn, int epi, int w_format, cons
 /* y = LayerNorm(x) over rows of 1280 (out_f16 != 0: fp16 output, else f32) */
 int hm_test_layernorm(hm_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y,
                       int rows, float eps, int out_f16, void* stream);
-/* attention core on a [B*192,3840] fp16 qkv buffer -> [B*192,1280] fp16 */
-int hm_test_attention(hm_ctx* ctx, const uint16_t* qkv, uint16_t* out, int B, void* stream);
+/* attention core on a [B*192,3840] fp16 qkv buffer -> [B*192,1280] fp16
+ * (variant 0 = mma.sync kernel, 1 = tcgen05/TMEM kernel, 2 = tcgen05 kernel that then overwrites the
+ * head of `out` with per-CTA phase clocks: 16 x int64 per (head, crop), diagnostics only) */
+int hm_test_attention(hm_ctx* ctx, int variant, const uint16_t* qkv, uint16_t* out, int B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,13 +87,14 @@ def test_layernorm(engine, rows, f16):
         assert torch.allclose(y.cpu(), ref, rtol=1e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize('variant', [1, 0])
 @pytest.mark.parametrize('B', [1, 3])
-def test_attention_core(engine, B):
+def test_attention_core(engine, B, variant):
     dev = engine.device
     g = torch.Generator(device=dev).manual_seed(B)
     qkv = (torch.randn(B * 192, 3840, generator=g, device=dev) * 1.5).half()
     out = torch.empty(B * 192, 1280, device=dev, dtype=torch.float16)
-    engine.check(engine.lib.hm_test_attention(engine.h, C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()),
+    engine.check(engine.lib.hm_test_attention(engine.h, variant, C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()),
                                               B, engine.stream()))
     q, k, v = qkv.float().cpu().reshape(B, 192, 3, 16, 80).permute(2, 0, 3, 1, 4)
     attn = ((q * 80 ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
