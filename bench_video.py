@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""BASELINE config[4]: end-to-end video stream, 1920x1080 frames, 2-8 hands per frame:
+crop warp + ViT-H + MANO + camera post-processing through hamer_inference.estimate_from_rgb
+(host frame in, results synchronised per frame); reports p50 / p99 latency per frame.
+
+    python bench_video.py [--frames 500] [--warmup 20]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def synthetic_frame(h, w, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], axis=-1)
+    return np.clip(base + rng.integers(-40, 40, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--frames', type=int, default=500)
+    ap.add_argument('--warmup', type=int, default=20)
+    args = ap.parse_args()
+    from hamer_yolo_b200 import load_hamer, hamer_inference, synthetic_mano
+    from hamer_yolo_b200.weights import random_state_dict
+    dev = torch.device('cuda', 0)
+    model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0),
+                          device=dev, max_batch=8)
+    hi = hamer_inference(model=model)
+    frames = [synthetic_frame(1080, 1920, s) for s in range(8)]
+    rng = np.random.default_rng(0)
+    k_real = np.array([[1400., 0, 960.], [0, 1400., 540.], [0, 0, 1]], np.float32)
+    lat, hands = [], []
+    for i in range(args.warmup + args.frames):
+        n = int(rng.integers(2, 9))
+        dets = []
+        for _ in range(n):
+            s = float(rng.integers(80, 401))
+            x1 = float(rng.integers(0, 1920 - 80)); y1 = float(rng.integers(0, 1080 - 80))
+            dets.append(['right' if rng.random() < 0.5 else 'left', [x1, y1, x1 + s, y1 + s * float(rng.uniform(0.8, 1.3))]])
+        frame = frames[i % len(frames)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, _ = hi.estimate_from_rgb(frame, dets, k_real)
+        verts = out['pred_vertices'].cpu()              # results on the host = end of the frame
+        kp = out['pred_keypoints_2d_full'].cpu()
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= args.warmup:
+            lat.append(dt); hands.append(n)
+    lat = np.array(lat)
+    line = {'metric': 'per-frame latency, 1920x1080, 2-8 hands/frame (crop warp + ViT-H + MANO)',
+            'unit': 'ms', 'frames': int(args.frames), 'p50_ms': float(np.percentile(lat, 50)),
+            'p99_ms': float(np.percentile(lat, 99)), 'mean_ms': float(lat.mean()),
+            'mean_hands_per_frame': float(np.mean(hands)), 'frames_per_s': float(1e3 / lat.mean()),
+            'hands_per_s': float(np.sum(hands) / (lat.sum() / 1e3)), 'higher_is_better': False,
+            'data': 'synthetic', 'config': {'workload': 'BASELINE config[4] video stream', 'n_gpus': 1,
+                                            'api': 'hamer_inference.estimate_from_rgb (host frame, per-frame sync)'}}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

@@ -36,7 +36,7 @@ class Engine:
     """Owns one hm_ctx (one device, one stream user).  Thin: argument marshalling only."""
 
     def __init__(self, device, max_batch=64, max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0,
-                 attention_legacy=0):
+                 attention_legacy=0, use_graphs=True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -52,8 +52,14 @@ class Engine:
         if rc != 0:
             raise _lib.HmError(rc, self.lib.hm_last_error(None).decode())
         self.h = h
+        # CUDA graphs of hm_forward, one per batch size (the path is ~310 launches; replaying a graph
+        # removes the launch gaps - most of the latency at the 2-8 hands of a video frame)
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}
+        self._profiling = False
 
     def close(self):
+        self._graphs = {}
         if getattr(self, 'h', None):
             self.lib.hm_destroy(self.h)
             self.h = None
@@ -107,9 +113,50 @@ class Engine:
             setattr(s, name, t[name][lo:hi].data_ptr() if name in t else None)
         return s
 
+    _FIELDS = (('pred_cam', (3,)), ('global_orient', (1, 3, 3)), ('hand_pose', (15, 3, 3)), ('betas', (10,)),
+               ('pred_cam_t', (3,)), ('focal_length', (2,)), ('pred_keypoints_3d', (21, 3)),
+               ('pred_vertices', (778, 3)), ('pred_keypoints_2d', (21, 2)))
+
+    def _views(self, flat, B):
+        t, off = {}, 0
+        for name, shp in self._FIELDS:
+            n = B * int(np.prod(shp))
+            t[name] = flat[off:off + n].view(B, *shp)
+            off += n
+        return t
+
+    def _forward_graph(self, img):
+        B = img.shape[0]
+        g = self._graphs.get(B)
+        if g is None:
+            per = sum(int(np.prod(shp)) for _, shp in self._FIELDS)
+            static_img = torch.empty(B, 3, IMG, IMG, device=self.device, dtype=torch.float32)
+            static_flat = torch.empty(B * per, device=self.device, dtype=torch.float32)
+            outs = self._views(static_flat, B)
+            s = self._struct(outs, 0, B)
+            static_img.copy_(img)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                      # warm-up outside capture (lazy func attributes)
+                self.check(self.lib.hm_forward(self.h, _ptr(static_img), B, C.byref(s), self.stream()))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.check(self.lib.hm_forward(self.h, _ptr(static_img), B, C.byref(s), self.stream()))
+            g = self._graphs[B] = (graph, static_img, static_flat)
+        graph, static_img, static_flat = g
+        static_img.copy_(img)
+        graph.replay()
+        return self._views(static_flat.clone(), B)             # results are the caller's own memory
+
     def forward(self, img, want_feats=False):
         """img: CUDA float32 [B,3,256,256].  Returns dict of CUDA tensors (hm_outputs fields)."""
         B = img.shape[0]
+        if (self.use_graphs and not want_feats and not self._profiling and B <= self.max_batch
+                and not torch.cuda.is_current_stream_capturing()):
+            with torch.cuda.device(self.device):
+                return self._forward_graph(img)
         t = self._outputs(B, want_feats)
         with torch.cuda.device(self.device):
             for lo in range(0, B, self.max_batch):          # transparently chunk large batches
@@ -179,6 +226,7 @@ class Engine:
         return int(self.lib.hm_forward_launch_count(self.h))
 
     def profile_enable(self, on=True):
+        self._profiling = bool(on)                             # per-launch events cannot be captured in a graph
         self.check(self.lib.hm_profile_enable(self.h, 1 if on else 0))
 
     def profile_collect(self):
@@ -195,11 +243,11 @@ class HAMER:
     dicts as hamer.py:124-156; tensors live on the model's CUDA device, float32."""
 
     def __init__(self, cfg=None, init_renderer=False, mano=None, device='cuda:0', max_batch=64,
-                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0):
+                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0, use_graphs=True):
         self.cfg = cfg if cfg is not None else default_config()
         if self.cfg.MODEL.IMAGE_SIZE != 256:
             raise AssertionError(f'MODEL.IMAGE_SIZE ({self.cfg.MODEL.IMAGE_SIZE}) should be 256 for ViT backbone')
-        self.engine = Engine(device, max_batch, max_frame_bytes, gemm_cta_group)
+        self.engine = Engine(device, max_batch, max_frame_bytes, gemm_cta_group, use_graphs=use_graphs)
         self.device = self.engine.device
         self.training = False
         if mano is None:
