@@ -160,6 +160,7 @@ def run_ours(args):
     model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0),
                           device=dev, max_batch=B)
     eng = model.engine
+    eng.use_graphs = not args.no_graphs
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     img = torch.randn(B, 3, 256, 256, generator=g, device=dev)
     img_host = img.cpu().pin_memory()
@@ -310,7 +311,11 @@ def run_ours(args):
                'sample': f'2 iterations x 8 crops (of the {B}-crop step), fp32 oracle of the reference PyTorch '
                          f'path, torch CPU with {cores} threads, {dt:.2f} s per iteration'}
 
-    launches = eng.launch_count() + 1 + (1 if world > 1 else 0)       # + output packing (+ all-gather)
+    launches = eng.launch_count() + 3 + (1 if world > 1 else 0)       # + input copy, result clone, packing (+ all-gather)
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('gemm_family_mean_mb_per_launch')
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -330,7 +335,7 @@ def run_ours(args):
                 'd2h_bytes_per_step': int(host_rec.numel() * 4)},
         'gpu_launches': launches * args.steps,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
-                     'frac': achieved / peaks['tf_sustained'], 'traffic': None,
+                     'frac': achieved / peaks['tf_sustained'], 'traffic': traffic, 'traffic_unit': 'MB per launch (ncu dram read+write, profiles/ncu_traffic.json)',
                      'kernel': 'gemm_bf16_tn_kernel (tcgen05/TMA GEMM, all epilogues; 129 launches per step)',
                      'peak_source': f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                      'per_family_tflops': per_family,
@@ -357,6 +362,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true', help='eager launches (for ncu launch lists)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -95,7 +95,6 @@ skinny_linear_kernel(const SkinnyParams p) {
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-
     float acc[SK_ROWS];
 #pragma unroll
     for (int r = 0; r < SK_ROWS; ++r) acc[r] = 0.f;
@@ -137,25 +136,35 @@ head_scores_kernel(const float* __restrict__ feats, const float* __restrict__ u,
     const float4* ub = reinterpret_cast<const float4*>(u + (size_t)b * 8 * 1280);
     for (int e = threadIdx.x; e < 8 * 320; e += 256) reinterpret_cast<float4*>(&us[0][0])[e] = ub[e];
     __syncthreads();
-    for (int tt = 0; tt < 4; ++tt) {
-        const int t = blockIdx.x * 32 + warp * 4 + tt;
-        const float4* f = reinterpret_cast<const float4*>(feats + ((size_t)b * 192 + t) * 1280);
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 2
-        for (int i = 0; i < 10; ++i) {
-            const float4 x = f[i * 32 + lane];
+    // a warp owns 4 context tokens and walks them together: every u float4 read from shared memory
+    // feeds 4 tokens (the kernel was bound by shared-memory reads with one token at a time)
+    const int t0 = blockIdx.x * 32 + warp * 4;
+    const float4* f = reinterpret_cast<const float4*>(feats + ((size_t)b * 192 + t0) * 1280);
+    float acc[4][8];
 #pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const float4 w = reinterpret_cast<const float4*>(&us[h][0])[i * 32 + lane];
-                acc[h] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[h]))));
-            }
-        }
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) acc[t][h] = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < 10; ++i) {
+        float4 x[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) x[t] = f[(size_t)t * 320 + i * 32 + lane];
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
-            const float v = warp_sum(acc[h]);
-            if (lane == 0) sc[((size_t)b * 8 + h) * 192 + t] = v;
+            const float4 w = reinterpret_cast<const float4*>(&us[h][0])[i * 32 + lane];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                acc[t][h] = fmaf(x[t].x, w.x, fmaf(x[t].y, w.y, fmaf(x[t].z, w.z, fmaf(x[t].w, w.w, acc[t][h]))));
         }
     }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float v = warp_sum(acc[t][h]);
+            if (lane == 0) sc[((size_t)b * 8 + h) * 192 + t0 + t] = v;
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,7 +175,7 @@ head_scores_kernel(const float* __restrict__ feats, const float* __restrict__ u,
 __global__ void __launch_bounds__(128)
 head_pool_kernel(const float* __restrict__ feats, const float* __restrict__ sc,
                  float* __restrict__ pooled) {
-    __shared__ float a[8][192];
+    __shared__ __align__(16) float a[192][8];          // [token][head]: two float4 broadcasts per token
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int h = warp; h < 8; h += 4) {               // each warp normalises two heads
         const float* s = sc + ((size_t)b * 8 + h) * 192;
@@ -179,17 +188,21 @@ head_pool_kernel(const float* __restrict__ feats, const float* __restrict__ sc,
         for (int i = 0; i < 6; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
         const float inv = 1.0f / warp_sum(sum);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) a[h][i * 32 + lane] = v[i] * inv;
+        for (int i = 0; i < 6; ++i) a[i * 32 + lane][h] = v[i] * inv;
     }
     __syncthreads();
     const int c = blockIdx.x * 128 + threadIdx.x;
     const float* f = feats + (size_t)b * 192 * 1280 + c;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 4
+#pragma unroll 8
     for (int t = 0; t < 192; ++t) {
         const float x = f[(size_t)t * 1280];
-#pragma unroll
-        for (int h = 0; h < 8; ++h) acc[h] = fmaf(a[h][t], x, acc[h]);
+        const float4 a0 = *reinterpret_cast<const float4*>(&a[t][0]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&a[t][4]);
+        acc[0] = fmaf(a0.x, x, acc[0]); acc[1] = fmaf(a0.y, x, acc[1]);
+        acc[2] = fmaf(a0.z, x, acc[2]); acc[3] = fmaf(a0.w, x, acc[3]);
+        acc[4] = fmaf(a1.x, x, acc[4]); acc[5] = fmaf(a1.y, x, acc[5]);
+        acc[6] = fmaf(a1.z, x, acc[6]); acc[7] = fmaf(a1.w, x, acc[7]);
     }
 #pragma unroll
     for (int h = 0; h < 8; ++h) pooled[((size_t)b * 8 + h) * 1280 + c] = acc[h];
