@@ -20,6 +20,7 @@
 #include "elementwise.cuh"
 #include "gemm_host.cuh"
 #include "mano_lbs.cuh"
+#include "mano_fused.cuh"
 
 using namespace hm;
 
@@ -33,7 +34,8 @@ constexpr int KPATCH = 1536;   // 2 x 768: [hi | lo] split of the fp32 pixels
 constexpr int HD = 1024;       // decoder width
 constexpr int HDEPTH = 6;
 constexpr int NREAD = 109;     // 96 pose6d + 10 betas + 3 cam
-constexpr int MANO_CHUNK = 8192;  // hands per MANO pass: 80 MB of fp32 v_posed stays inside the 126 MB L2
+constexpr int MANO_CHUNK = 8192;  // legacy 3-kernel path: hands per pass (80 MB of fp32 v_posed stays inside the 126 MB L2)
+constexpr int MANO_FCHUNK = 65536; // fused path: hands per launch (71 MB of coefficient / transform workspace)
 
 std::string g_create_error;
 
@@ -114,6 +116,11 @@ struct hm_ctx {
     __half* m_coef = nullptr;     // [MANO_CHUNK, 320]
     float *m_vposed = nullptr, *m_A = nullptr, *m_jpos = nullptr;
     CUtensorMap tm_mcoef, tm_mbasis;
+    __half* mf_coef = nullptr;    // [MANO_FCHUNK, 160]
+    float* mf_Au = nullptr;       // [MANO_FCHUNK/128][16][128][12]
+    CUtensorMap tm_fcoef, tm_fbasis;
+    bool mano_fused_ok = false;   // joint_map is a permutation (every source joint has exactly one slot)
+    bool mano_legacy = false;
 
     // preprocess
     uint8_t* frame_dev = nullptr;
@@ -392,15 +399,67 @@ int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaS
     return HM_OK;
 }
 
+// Work units per 256-hand tile for the fused kernel: more units fill the GPU at small B and trim the
+// last wave at large B; each unit re-loads the tile's coefficients / transforms (cost ~1.5 coordinate tiles).
+int mano_pick_split(int pair_tiles, int workers) {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ns = 1; ns <= MF_NT; ++ns) {
+        const int waves = (pair_tiles * ns + workers - 1) / workers;
+        const double cost = waves * ((MF_NT + ns - 1) / ns + 1.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+    }
+    return best;
+}
+
+int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
+                   float* verts, float* joints, float* kp2d, cudaStream_t s) {
+    const bool proj = cam_t != nullptr && kp2d != nullptr;
+    for (int lo = 0; lo < B; lo += MANO_FCHUNK) {
+        const int n = (B - lo < MANO_FCHUNK) ? (B - lo) : MANO_FCHUNK;
+        ManoPrepArgs pa{};
+        pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
+        pa.coef = c->mf_coef; pa.A = c->mf_Au; pa.jpos = nullptr; pa.B = n;
+        pa.joints = joints + (size_t)lo * 63;
+        pa.kp2d = proj ? kp2d + (size_t)lo * 42 : nullptr;
+        pa.cam_t = proj ? cam_t + (size_t)lo * 3 : nullptr;
+        pa.focal_over_size = 5000.0f / 256.0f;
+        mano_prep_kernel<true><<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
+        ManoFusedArgs a{};
+        a.Au = c->mf_Au; a.cam_t = pa.cam_t; a.verts = verts + (size_t)lo * MANO_V * 3;
+        a.joints = pa.joints; a.kp2d = pa.kp2d; a.focal_over_size = pa.focal_over_size; a.B = n;
+        const int pair_tiles = (n + 2 * MF_BM - 1) / (2 * MF_BM);
+        const int workers_max = c->num_sms / 2;
+        a.n_split = mano_pick_split(pair_tiles, workers_max);
+        const int units = pair_tiles * a.n_split;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (units < workers_max ? units : workers_max));
+        cfg.blockDim = dim3(MF_THREADS);
+        cfg.dynamicSmemBytes = MF_SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        HM_CUDA(c, cudaLaunchKernelEx(&cfg, mano_fused_kernel, c->tm_fcoef, c->tm_fbasis, c->mano, a));
+    }
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
 int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
              float* verts, float* joints, float* kp2d, cudaStream_t s) {
     ProfScope ps(c, s, PC_MANO_LBS);
+    // the fused kernel stores vertices with 8-byte vector stores
+    if (c->mano_fused_ok && !c->mano_legacy && (reinterpret_cast<uintptr_t>(verts) & 7u) == 0)
+        return lbs_fused_impl(c, betas, rotmats, cam_t, B, verts, joints, kp2d, s);
     for (int lo = 0; lo < B; lo += MANO_CHUNK) {                 // chunk: v_posed stays L2-resident
         const int n = (B - lo < MANO_CHUNK) ? (B - lo) : MANO_CHUNK;
-        ManoPrepArgs pa;
+        ManoPrepArgs pa{};
         pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
         pa.coef = c->m_coef; pa.A = c->m_A; pa.jpos = c->m_jpos; pa.B = n;
-        mano_prep_kernel<<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
+        mano_prep_kernel<false><<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
         GemmParams p;
         p.M = n; p.N = MANO_NPAD; p.K = MANO_KTOT; p.bias = c->mano.template_n; p.out = c->m_vposed;
         p.ldo = MANO_NPAD; p.pos = c->mano.zero_row; p.pos_rows = 1; p.b_format = 0;
@@ -458,6 +517,7 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     c->plan.bn = 256;
     c->b_format = 0u;   // fp16 weight operands (kind::f16 requires A and B of the same 16-bit type)
     c->att_legacy = cfg->attention_legacy != 0;
+    c->mano_legacy = cfg->mano_legacy != 0;
     if (!get_tmap_encode()) return bail(HM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
     const size_t Mmax = (size_t)cfg->max_batch * TOK, Bm = (size_t)cfg->max_batch;
@@ -523,7 +583,9 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
         cudaFuncSetAttribute(vit_attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)AT5_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(mano_skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(SkinSmem)) != cudaSuccess)
+                             (int)sizeof(SkinSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(mano_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)MF_SMEM_BYTES) != cudaSuccess)
         return bail(HM_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
     *out = c;
     return HM_OK;
@@ -749,6 +811,15 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
                 basis16[(size_t)n * MANO_KTOT + MANO_KB + k] = lo;
             }
         }
+    // fused kernel: same basis with the rows of each 16-vertex group ordered (x0 x1 y0 y1 z0 z1) per vertex pair,
+    // so that the accumulator columns a thread reads are packed pairs for FFMA2
+    std::vector<__half> basis16f((size_t)MANO_NPAD * MANO_KTOT, __float2half(0.f));
+    for (int v = 0; v < MANO_V; ++v)
+        for (int cdim = 0; cdim < 3; ++cdim) {
+            const int i = v % MF_GV;
+            const size_t nf = (size_t)(v / MF_GV) * MF_GCOLS + 6 * (i >> 1) + 2 * cdim + (i & 1);
+            memcpy(&basis16f[nf * MANO_KTOT], &basis16[(size_t)(v * 3 + cdim) * MANO_KTOT], MANO_KTOT * sizeof(__half));
+        }
     // folded joint regressor (double accumulation; one-time)
     std::vector<float> jt(48), js(480);
     for (int j = 0; j < 16; ++j)
@@ -791,6 +862,44 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
             }
         wnu[w] = nu;
     }
+    // fused kernel: union of joints + weights per 16-vertex group (warp-uniform in the epilogue)
+    std::vector<float> ftab((size_t)MF_GROUPS * MF_TAB_F4 * 4, 0.f);
+    for (int g = 0; g < MF_GROUPS; ++g) {
+        float* tab = ftab.data() + (size_t)g * MF_TAB_F4 * 4;
+        int32_t* tabi = reinterpret_cast<int32_t*>(tab);
+        uint32_t um = 0;
+        for (int i = 0; i < MF_GV; ++i) {
+            const int v = g * MF_GV + i;
+            if (v >= MANO_V) continue;
+            um |= mask[v];
+            for (int cdim = 0; cdim < 3; ++cdim) tab[6 * (i >> 1) + 2 * cdim + (i & 1)] = v_template[v * 3 + cdim];
+        }
+        for (int q = 0; q < 5; ++q) if (tip_ids[q] / MF_GV == g) tabi[65] |= 1 << q;
+        int nu = 0;
+        for (int j = 0; j < 16; ++j)
+            if (um & (1u << j)) {
+                tabi[48 + nu] = j;
+                for (int i = 0; i < MF_GV; ++i) {
+                    const int v = g * MF_GV + i;
+                    if (v < MANO_V) tab[128 + nu * 16 + i] = lbs_weights[v * 16 + j];
+                    if (v < MANO_V && lbs_weights[v * 16 + j] != 0.f) tabi[80 + nu] |= 1 << (i >> 1);
+                }
+                ++nu;
+            }
+        tabi[64] = nu;
+    }
+    {   // output slots: joint_map[k] = source (0..15 chain joint, 16..20 fingertip)
+        int count[21] = {0};
+        for (int j = 0; j < 16; ++j) c->mano.chain_slot[j] = -1;
+        for (int q = 0; q < 5; ++q) c->mano.tip_slot[q] = -1;
+        for (int k = 0; k < 21; ++k) {
+            const int src = joint_map[k];
+            ++count[src];
+            if (src < 16) c->mano.chain_slot[src] = k; else c->mano.tip_slot[src - 16] = k;
+        }
+        c->mano_fused_ok = true;
+        for (int q = 0; q < 21; ++q) if (count[q] != 1) c->mano_fused_ok = false;   // not a permutation: 3-kernel path
+    }
     for (void* p : c->mano_allocs) cudaFree(p);
     c->mano_allocs.clear();
     c->mano_set = false;
@@ -803,6 +912,7 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         return cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
     };
     HM_CUDA(c, up(basis16.data(), basis16.size() * 2, reinterpret_cast<const void**>(&c->mano.basis16)));
+    HM_CUDA(c, up(basis16f.data(), basis16f.size() * 2, reinterpret_cast<const void**>(&c->mano.basis16f)));
     HM_CUDA(c, up(tmpl.data(), tmpl.size() * 4, reinterpret_cast<const void**>(&c->mano.template_n)));
     HM_CUDA(c, up(zrow.data(), zrow.size() * 4, reinterpret_cast<const void**>(&c->mano.zero_row)));
     HM_CUDA(c, up(jt.data(), jt.size() * 4, reinterpret_cast<const void**>(&c->mano.j_template)));
@@ -811,6 +921,7 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
     HM_CUDA(c, up(wnu.data(), wnu.size() * 4, reinterpret_cast<const void**>(&c->mano.warp_nu)));
     HM_CUDA(c, up(wun.data(), wun.size() * 4, reinterpret_cast<const void**>(&c->mano.warp_union)));
     HM_CUDA(c, up(lw.data(), lw.size() * 4, reinterpret_cast<const void**>(&c->mano.lane_w)));
+    HM_CUDA(c, up(ftab.data(), ftab.size() * 4, reinterpret_cast<const void**>(&c->mano.fz_tab)));
     // per-chunk workspace (coefficients, v_posed, skinning transforms, posed joints) + tensor maps
     {
         void* d = nullptr;
@@ -823,6 +934,14 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         if (!make_tmap_bf16_2d(&c->tm_mcoef, c->m_coef, ch, MANO_KTOT, MANO_KTOT, GEMM_BM) ||
             !make_tmap_bf16_2d(&c->tm_mbasis, c->mano.basis16, MANO_NPAD, MANO_KTOT, MANO_KTOT, 128 / c->plan.cta_group))
             return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed");
+        const size_t fc = MANO_FCHUNK;
+        HM_CUDA(c, cudaMalloc(&d, fc * MANO_KB * 2)); c->mano_allocs.push_back(d); c->mf_coef = reinterpret_cast<__half*>(d);
+        HM_CUDA(c, cudaMemset(c->mf_coef, 0, fc * MANO_KB * 2));
+        HM_CUDA(c, cudaMalloc(&d, fc * MANO_J * 48)); c->mano_allocs.push_back(d); c->mf_Au = reinterpret_cast<float*>(d);
+        HM_CUDA(c, cudaMemset(c->mf_Au, 0, fc * MANO_J * 48));
+        if (!make_tmap_bf16_2d(&c->tm_fcoef, c->mf_coef, fc, MANO_KB, MANO_KB, MF_BM) ||
+            !make_tmap_bf16_2d(&c->tm_fbasis, c->mano.basis16f, MANO_NPAD, MANO_KTOT, MANO_KTOT, MF_BN / 2))
+            return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed (fused)");
     }
     for (int j = 0; j < 16; ++j) c->mano.parents[j] = parents[j];
     for (int q = 0; q < 5; ++q) c->mano.tip_ids[q] = tip_ids[q];
@@ -940,10 +1059,10 @@ int hm_forward(hm_ctx* c, const float* img, int B, const hm_outputs* out, void* 
                     out->pred_keypoints_2d, s);
 }
 
-int hm_forward_launch_count(const hm_ctx*) {
+int hm_forward_launch_count(const hm_ctx* ctx) {
     // im2col + patch GEMM + 32 x (LN, qkv, attention, proj, LN, fc1, fc2) + last LN
-    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO (prep, blend GEMM, skinning)
-    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + 3;
+    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO (prep, fused blend + skinning)
+    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + ((ctx && (ctx->mano_legacy || !ctx->mano_fused_ok)) ? 3 : 2);
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------

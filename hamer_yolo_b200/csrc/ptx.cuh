@@ -149,6 +149,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (size and both addresses multiples of 16 B), completion on an
+// mbarrier of the executing CTA.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // smem tile -> global with an fp32 add performed at L2 (out += tile): the residual stream is never
 // read by the SM.  Bulk-group completion: commit, then wait (.read = smem reusable, plain = done).
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src,

@@ -36,7 +36,7 @@ class Engine:
     """Owns one hm_ctx (one device, one stream user).  Thin: argument marshalling only."""
 
     def __init__(self, device, max_batch=64, max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0,
-                 attention_legacy=0, use_graphs=True):
+                 attention_legacy=0, mano_legacy=0, use_graphs=True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -46,7 +46,8 @@ class Engine:
         self.max_batch = int(max_batch)
         self.max_frame_bytes = int(max_frame_bytes)
         cfg = _lib.HmConfig(max_batch=self.max_batch, max_frame_bytes=self.max_frame_bytes,
-                            gemm_cta_group=int(gemm_cta_group), attention_legacy=int(attention_legacy))
+                            gemm_cta_group=int(gemm_cta_group), attention_legacy=int(attention_legacy),
+                            mano_legacy=int(mano_legacy))
         h = C.c_void_p()
         rc = self.lib.hm_create(C.byref(h), self.index, C.byref(cfg))
         if rc != 0:

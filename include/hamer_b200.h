@@ -41,7 +41,8 @@ typedef struct hm_config {
     int32_t max_frame_bytes;  /* largest H*row_stride accepted by hm_preprocess (host frames) */
     int32_t gemm_cta_group;   /* 0 = default (2: CTA-pair UMMA M=256), 1 = single-CTA tiles */
     int32_t attention_legacy; /* 0 = tcgen05/TMEM attention kernel (default), 1 = mma.sync kernel */
-    int32_t reserved[4];
+    int32_t mano_legacy;      /* 0 = fused tcgen05 blend + skinning kernel (default), 1 = prep / GEMM / skinning kernels */
+    int32_t reserved[3];
 } hm_config;
 
 /* Device pointers of the tensors HAMER.forward_step returns (hamer/hamer/models/hamer.py:124-156).

@@ -174,7 +174,7 @@ def random_mano_inputs(B, seed):
     return betas, rot, cam_t
 
 
-@pytest.mark.parametrize('B', [1, 16, 37])
+@pytest.mark.parametrize('B', [1, 16, 37, 300])
 def test_mano_lbs_vs_oracle(engine, oracle_model, B):
     from oracle.mano import mano_forward
     from oracle.pipeline import perspective_projection
@@ -186,6 +186,23 @@ def test_mano_lbs_vs_oracle(engine, oracle_model, B):
     assert (verts.cpu() - v_ref).norm(dim=-1).max().item() < 0.02 * MM         # 0.02 mm (fp16 blend coefficients)
     assert (joints.cpu() - j_ref).norm(dim=-1).max().item() < 0.02 * MM
     assert (kp2d.cpu() - k_ref).abs().max().item() * 256 < 0.01                # px
+
+
+def test_mano_lbs_three_kernel_path_agrees(engine, oracle_model):
+    """hm_config.mano_legacy selects the prep / GEMM / skinning kernels: same numbers as the fused kernel
+    up to fp32 re-association of the skinning sum."""
+    from hamer_yolo_b200.hamer import Engine
+    betas, rot, cam_t = random_mano_inputs(700, 3)
+    dev = engine.device
+    v, j, k = engine.mano_lbs(betas.to(dev), rot.to(dev), cam_t.to(dev))
+    eng = Engine('cuda:0', max_batch=2, mano_legacy=1)
+    try:
+        eng.set_mano(oracle_model.mano_data)
+        v2, j2, k2 = eng.mano_lbs(betas.to(dev), rot.to(dev), cam_t.to(dev))
+    finally:
+        eng.close()
+    assert (v - v2).abs().max().item() < 2e-6 and (j - j2).abs().max().item() < 2e-6
+    assert (k - k2).abs().max().item() * 256 < 1e-3
 
 
 def test_mano_lbs_full_size_properties(engine):
