@@ -118,7 +118,7 @@ struct hm_ctx {
     CUtensorMap tm_mcoef, tm_mbasis;
     __half* mf_coef = nullptr;    // [MANO_FCHUNK, 160]
     float* mf_Au = nullptr;       // [MANO_FCHUNK/128][16][128][12]
-    CUtensorMap tm_fcoef, tm_fbasis;
+    CUtensorMap tm_fbasis;
     bool mano_fused_ok = false;   // joint_map is a permutation (every source joint has exactly one slot)
     bool mano_legacy = false;
 
@@ -426,11 +426,13 @@ int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const fl
         pa.focal_over_size = 5000.0f / 256.0f;
         mano_prep_kernel<true><<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
         ManoFusedArgs a{};
-        a.Au = c->mf_Au; a.cam_t = pa.cam_t; a.verts = verts + (size_t)lo * MANO_V * 3;
+        a.coef = c->mf_coef; a.Au = c->mf_Au; a.cam_t = pa.cam_t; a.verts = verts + (size_t)lo * MANO_V * 3;
         a.joints = pa.joints; a.kp2d = pa.kp2d; a.focal_over_size = pa.focal_over_size; a.B = n;
         const int pair_tiles = (n + 2 * MF_BM - 1) / (2 * MF_BM);
         const int workers_max = c->num_sms / 2;
         a.n_split = mano_pick_split(pair_tiles, workers_max);
+        static const int mano_dbg = [] { const char* e = getenv("HM_MANO_DBG"); return e ? atoi(e) : 0; }();
+        a.dbg = mano_dbg;   // kernel ablation switches for profiling (see ManoFusedArgs::dbg); 0 in normal use
         const int units = pair_tiles * a.n_split;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * (units < workers_max ? units : workers_max));
@@ -442,7 +444,7 @@ int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const fl
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        HM_CUDA(c, cudaLaunchKernelEx(&cfg, mano_fused_kernel, c->tm_fcoef, c->tm_fbasis, c->mano, a));
+        HM_CUDA(c, cudaLaunchKernelEx(&cfg, mano_fused_kernel, c->tm_fbasis, c->mano, a));
     }
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
@@ -874,19 +876,20 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
             um |= mask[v];
             for (int cdim = 0; cdim < 3; ++cdim) tab[6 * (i >> 1) + 2 * cdim + (i & 1)] = v_template[v * 3 + cdim];
         }
-        for (int q = 0; q < 5; ++q) if (tip_ids[q] / MF_GV == g) tabi[65] |= 1 << q;
+        for (int q = 0; q < 5; ++q) if (tip_ids[q] / MF_GV == g) tabi[25] |= 1 << q;
         int nu = 0;
         for (int j = 0; j < 16; ++j)
             if (um & (1u << j)) {
-                tabi[48 + nu] = j;
+                tabi[32 + nu] = 12 * j;
                 for (int i = 0; i < MF_GV; ++i) {
                     const int v = g * MF_GV + i;
-                    if (v < MANO_V) tab[128 + nu * 16 + i] = lbs_weights[v * 16 + j];
-                    if (v < MANO_V && lbs_weights[v * 16 + j] != 0.f) tabi[80 + nu] |= 1 << (i >> 1);
+                    if (v >= MANO_V || lbs_weights[v * 16 + j] == 0.f) continue;
+                    tab[64 + nu * MF_GV + i] = lbs_weights[v * 16 + j];
+                    tabi[32 + nu] |= 1 << (16 + (i >> 1));
                 }
                 ++nu;
             }
-        tabi[64] = nu;
+        tabi[24] = nu;
     }
     {   // output slots: joint_map[k] = source (0..15 chain joint, 16..20 fingertip)
         int count[21] = {0};
@@ -939,8 +942,7 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         HM_CUDA(c, cudaMemset(c->mf_coef, 0, fc * MANO_KB * 2));
         HM_CUDA(c, cudaMalloc(&d, fc * MANO_J * 48)); c->mano_allocs.push_back(d); c->mf_Au = reinterpret_cast<float*>(d);
         HM_CUDA(c, cudaMemset(c->mf_Au, 0, fc * MANO_J * 48));
-        if (!make_tmap_bf16_2d(&c->tm_fcoef, c->mf_coef, fc, MANO_KB, MANO_KB, MF_BM) ||
-            !make_tmap_bf16_2d(&c->tm_fbasis, c->mano.basis16f, MANO_NPAD, MANO_KTOT, MANO_KTOT, MF_BN / 2))
+        if (!make_tmap_bf16_2d(&c->tm_fbasis, c->mano.basis16f, MANO_NPAD, MANO_KTOT, MANO_KTOT, MF_BN / 2))
             return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed (fused)");
     }
     for (int j = 0; j < 16; ++j) c->mano.parents[j] = parents[j];
