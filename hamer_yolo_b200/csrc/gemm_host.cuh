@@ -97,6 +97,17 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
     const int tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BN);
     int workers = num_sms / CTA_GROUP;
     if (tiles < workers) workers = tiles;
+    GemmParams pp = p;
+    pp.ksplit = 1;
+    if (EPI == EPI_BIAS_RESID_F32 && tiles > workers && tiles % workers != 0) {
+        // K-slices for the tail tiles: as many as there are workers per tail tile, at least 4 k-blocks each
+        const int tail = tiles % workers;
+        int ks = workers / tail;
+        const int num_k = p.K / GEMM_BK;
+        if (ks > num_k / 4) ks = num_k / 4;
+        if (ks > 8) ks = 8;
+        if (ks >= 2 && p.ksplit >= 0) pp.ksplit = ks;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * CTA_GROUP);
     cfg.blockDim = dim3(Cfg::THREADS);
@@ -109,7 +120,7 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p);
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, pp);
 }
 
 template <int CTA_GROUP, int BN>

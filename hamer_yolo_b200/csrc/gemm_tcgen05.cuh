@@ -51,7 +51,21 @@ struct GemmParams {
     int ldo;            // elements
     const float* pos;   // [pos_rows, N] (EPI_BIAS_POS_F32)
     int pos_rows;
+    int ksplit;         // EPI_BIAS_RESID_F32 only: the tiles of the last, partial wave are split into `ksplit`
+                        // K-slices (each slice reduce-adds its partial product; slice 0 carries the bias); <= 1 = off
 };
+
+// Work items of the persistent loop: full tiles first, then the K-slices of the tail tiles.
+struct GemmItem { int tile, kb0, kb1; };
+__device__ __forceinline__ GemmItem gemm_item(int item, int full_tiles, int ksplit, int num_k) {
+    GemmItem it;
+    if (item < full_tiles) { it.tile = item; it.kb0 = 0; it.kb1 = num_k; return it; }
+    const int r = item - full_tiles, t = r / ksplit, sl = r - t * ksplit;
+    it.tile = full_tiles + t;
+    it.kb0 = sl * num_k / ksplit;
+    it.kb1 = (sl + 1) * num_k / ksplit;
+    return it;
+}
 
 constexpr int GEMM_BM = 128;  // rows per CTA (UMMA M = 128 * CTA_GROUP)
 constexpr int GEMM_BK = 64;   // 64 x 16-bit = 128 B = one swizzle atom row
@@ -160,6 +174,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int num_tiles = m_blocks * n_blocks;
     const int worker = blockIdx.x / CTA_GROUP;
     const int num_workers = gridDim.x / CTA_GROUP;
+    // wave quantisation: N = 1280 gives 240 tiles for 74 CTA pairs (3.24 waves); the 18 tiles of the last wave
+    // are split along K so that every worker gets a quarter tile instead of 18 workers a whole one
+    const bool split = (EPI == EPI_BIAS_RESID_F32) && p.ksplit > 1 && (num_tiles % num_workers) != 0 && num_tiles > num_workers;
+    const int ksplit = split ? p.ksplit : 1;
+    const int full_tiles = split ? (num_tiles / num_workers) * num_workers : num_tiles;
+    const int num_items = full_tiles + (num_tiles - full_tiles) * ksplit;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -188,11 +208,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = worker; tile < num_tiles; tile += num_workers) {
-                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            for (int item = worker; item < num_items; item += num_workers) {
+                const GemmItem wi = gemm_item(item, full_tiles, ksplit, num_k);
+                const int m_blk = wi.tile / n_blocks, n_blk = wi.tile % n_blocks;
                 const int m0 = m_blk * tile_m + (int)cta_rank * GEMM_BM;
                 const int n0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
-                for (int kb = 0; kb < num_k; ++kb) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if constexpr (CTA_GROUP == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -221,11 +242,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+            for (int item = worker; item < num_items; item += num_workers) {
+                const GemmItem wi = gemm_item(item, full_tiles, ksplit, num_k);
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_k; ++kb) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint64_t a_desc =
@@ -237,7 +259,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         // advance 16 elements (32 B) along K inside the 128 B swizzle atom
                         const uint64_t koff = (uint64_t)((k * GEMM_UMMA_K * 2) >> 4);
                         ptx::mma_f16<CTA_GROUP>(d_tmem, a_desc + koff, b_desc + koff, idesc,
-                                                (uint32_t)((kb | k) != 0));
+                                                (uint32_t)(kb != wi.kb0 || k != 0));
                     }
                     if constexpr (CTA_GROUP == 1) ptx::mma_commit_1sm(&empty_bar[stage]);
                     else ptx::mma_commit_2sm(&empty_bar[stage], 0x3);
@@ -259,8 +281,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t chunk_no = 0;                  // running count of staged chunks (double buffering)
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int item = worker; item < num_items; item += num_workers) {
+            const GemmItem wi = gemm_item(item, full_tiles, ksplit, num_k);
+            const bool with_bias = wi.kb0 == 0;                       // K-slices after the first add only their product
+            const int m_blk = wi.tile / n_blocks, n_blk = wi.tile % n_blocks;
             const int row0 = m_blk * tile_m + (int)cta_rank * GEMM_BM + quad * 32;
             const int row = row0 + lane;
             const int col0 = n_blk * BN + part * COLS_PER_WARP;
@@ -314,7 +338,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 b = __ldg(bias4 + j);
+                        const float4 b = with_bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                         float4 v;
                         v.x = __uint_as_float(r[j * 4 + 0]) + b.x; v.y = __uint_as_float(r[j * 4 + 1]) + b.y;
                         v.z = __uint_as_float(r[j * 4 + 2]) + b.z; v.w = __uint_as_float(r[j * 4 + 3]) + b.w;

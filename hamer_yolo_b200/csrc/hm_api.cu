@@ -315,7 +315,7 @@ cudaError_t launch_skinny(int epi, const float* X, int ldx, long long x_bs, cons
 
 int run_gemm(hm_ctx* c, int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
              const float* bias, void* out, const float* pos, cudaStream_t s) {
-    GemmParams p;
+    GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
     p.b_format = c->b_format;
     HM_CUDA(c, gemm_launch(c->plan, epi, ta, tb, c->tm_x_out, p, c->num_sms, s));
@@ -462,7 +462,7 @@ int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* c
         pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
         pa.coef = c->m_coef; pa.A = c->m_A; pa.jpos = c->m_jpos; pa.B = n;
         mano_prep_kernel<false><<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
-        GemmParams p;
+        GemmParams p{};
         p.M = n; p.N = MANO_NPAD; p.K = MANO_KTOT; p.bias = c->mano.template_n; p.out = c->m_vposed;
         p.ldo = MANO_NPAD; p.pos = c->mano.zero_row; p.pos_rows = 1; p.b_format = 0;
         GemmPlan plan{c->plan.cta_group, 128};
@@ -1079,7 +1079,7 @@ int hm_test_gemm(hm_ctx* c, int cta_group, int bn, int epi, int w_format, const 
     tout = ta;
     if (epi == EPI_BIAS_RESID_F32 && !make_tmap_f32_out(&tout, out, M, N, N))
         return fail(c, HM_ERR_CUDA, "hm_test_gemm: output tensor map encoding failed");
-    GemmParams p;
+    GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
     p.b_format = w_format ? 1u : 0u;
     GemmPlan plan{cta_group == 1 ? 1 : 2, bn};

@@ -107,7 +107,7 @@ int main(int argc, char** argv) {
         return 2;
     }
     const bool f32_out = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_POS_F32);
-    GemmParams p;
+    GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.bias = dbias;
     p.out = f32_out ? (void*)dout_f : (void*)dout_h;
@@ -115,6 +115,7 @@ int main(int argc, char** argv) {
     p.pos = dpos;
     p.pos_rows = 192;
     p.b_format = (uint32_t)w_fmt;
+    p.ksplit = getenv("HM_NO_KSPLIT") ? -1 : 0;   // -1: keep whole tiles in the tail wave (A/B timing)
     GemmPlan plan = {cg, bn};
     CK(gemm_launch(plan, epi, ta, tb, tout, p, num_sms, 0));
     CK(cudaDeviceSynchronize());
