@@ -815,12 +815,15 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         }
     // fused kernel: same basis with the rows of each 16-vertex group ordered (x0 x1 y0 y1 z0 z1) per vertex pair,
     // so that the accumulator columns a thread reads are packed pairs for FFMA2
-    std::vector<__half> basis16f((size_t)MANO_NPAD * MANO_KTOT, __float2half(0.f));
+    std::vector<__half> basis16f((size_t)MANO_NPAD * MANO_KB, __float2half(0.f));
     for (int v = 0; v < MANO_V; ++v)
         for (int cdim = 0; cdim < 3; ++cdim) {
             const int i = v % MF_GV;
             const size_t nf = (size_t)(v / MF_GV) * MF_GCOLS + 6 * (i >> 1) + 2 * cdim + (i & 1);
-            memcpy(&basis16f[nf * MANO_KTOT], &basis16[(size_t)(v * 3 + cdim) * MANO_KTOT], MANO_KTOT * sizeof(__half));
+            const __half* src = &basis16[(size_t)(v * 3 + cdim) * MANO_KTOT];
+            __half* dst = &basis16f[nf * MANO_KB];
+            for (int k = 0; k < 145; ++k) dst[k] = src[k];                     // shape hi | pose (fp16-rounded)
+            for (int k = 0; k < 10; ++k) dst[145 + k] = src[MANO_KB + k];      // shape lo, multiplied by the repeated betas
         }
     // folded joint regressor (double accumulation; one-time)
     std::vector<float> jt(48), js(480);
@@ -942,7 +945,7 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         HM_CUDA(c, cudaMemset(c->mf_coef, 0, fc * MANO_KB * 2));
         HM_CUDA(c, cudaMalloc(&d, fc * MANO_J * 48)); c->mano_allocs.push_back(d); c->mf_Au = reinterpret_cast<float*>(d);
         HM_CUDA(c, cudaMemset(c->mf_Au, 0, fc * MANO_J * 48));
-        if (!make_tmap_bf16_2d(&c->tm_fbasis, c->mano.basis16f, MANO_NPAD, MANO_KTOT, MANO_KTOT, MF_BN / 2))
+        if (!make_tmap_bf16_2d(&c->tm_fbasis, c->mano.basis16f, MANO_NPAD, MANO_KB, MANO_KB, MF_BN / 2))
             return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed (fused)");
     }
     for (int j = 0; j < 16; ++j) c->mano.parents[j] = parents[j];

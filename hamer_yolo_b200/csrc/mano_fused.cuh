@@ -12,11 +12,13 @@
 //                Transforms and coefficients are written once per unit (global -> registers -> tcgen05.st)
 //                and read by tcgen05.ld / as the MMA's A operand: they cost no shared-memory bandwidth,
 //                which is what bounds this kernel.
-//   MMA        : D[256 x 96] = coef[256 x 160] x (B_hi + B_lo)^T as 20 k-steps, A from tensor memory (the A
-//                address of k-step t is the coefficient slice t mod 10, so [a | a] is never materialised), B =
-//                the constant basis [2400 x 320] ([hi | lo] fp16 split, L2-resident) streamed by TMA; one ring
-//                stage is one whole coordinate tile (five 48-row x 64-column boxes per CTA), so the issuing
-//                thread pays one barrier wait and one commit per 20 MMAs.
+//   MMA        : D[256 x 96] = coef[256 x 160] x basis^T as 10 k-steps, A from tensor memory, B = the constant
+//                fp16 basis [2400 x 160] (L2-resident) streamed by TMA; one ring stage is one whole coordinate
+//                tile (three 48-row x 64-column boxes per CTA), so the issuing thread pays one barrier wait and
+//                one commit per 10 MMAs.  K layout: [shape hi (10) | pose (135) | shape lo (10) | 0 (5)] with the
+//                betas repeated under "shape lo": the shape basis is exact to 2^-22, the pose basis is rounded to
+//                fp16 (<= 0.004 mm on MANO, tests/tools note in DESIGN.md) - half the MMAs, basis traffic and
+//                shared-memory reads of a full [hi | lo] split.
 //   epilogue   : 16 warps, thread = hand (TMEM lane), 8 vertices per thread per tile.  v_posed =
 //                accumulator + template; out_v = sum_u w_vu (R_u p_v + t_u) over the union of joints of
 //                the 8-vertex group - weights and joint ids are warp-uniform (broadcast reads of a 768-byte
@@ -42,13 +44,13 @@ constexpr int MF_GCOLS = MF_GV * 3;        // 24 accumulator columns per thread 
 constexpr int MF_PARTS = MF_BN / MF_GCOLS; // 4 column slices per tile
 constexpr int MF_GROUPS = MF_NT * MF_PARTS;// 8-vertex groups (the last two are padding)
 constexpr int MF_KSTEPS = MANO_KB / 16;    // 10 UMMA k-steps per basis half
-constexpr int MF_KBLOCKS = MANO_KTOT / 64; // 5 basis blocks (64 columns) per tile
+constexpr int MF_KBLOCKS = (MANO_KB + 63) / 64; // 3 basis boxes of 64 columns per tile (the last one half used)
 constexpr int MF_BSTAGES = 4;              // one stage = one whole coordinate tile: with one k-block per stage the issuing
                                            // thread, not the tensor pipe, bounded the kernel (450 cycles per 4 MMAs of 41)
 constexpr int MF_EPI_WARPS = 4 * MF_PARTS; // 16: four TMEM lane quadrants x four column slices
 constexpr int MF_THREADS = 128 + 32 * MF_EPI_WARPS;   // warpgroup 0: producer, MMA issuer (+2 idle warps); 1-4: epilogue
 constexpr uint32_t MF_B_BLOCK = (MF_BN / 2) * 128;            // 48 basis rows x 64 columns
-constexpr uint32_t MF_B_STAGE = MF_KBLOCKS * MF_B_BLOCK;      // 30 KB per CTA per coordinate tile
+constexpr uint32_t MF_B_STAGE = MF_KBLOCKS * MF_B_BLOCK;      // 18 KB per CTA per coordinate tile
 constexpr uint32_t MF_WARP_STAGE = 32 * MF_GCOLS * 4;         // 3,072 B per epilogue warp: 32 dense rows of 24 floats
 constexpr uint32_t MF_STAGING = MF_EPI_WARPS * MF_WARP_STAGE;
 constexpr uint32_t MF_OFF_STAGING = MF_BSTAGES * MF_B_STAGE;
@@ -134,7 +136,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                         ptx::mbar_wait(&empty_b[stage], phase ^ 1u);
                         if (is_leader) ptx::mbar_arrive_expect_tx(&full_b[stage], 2 * MF_B_STAGE);
 #pragma unroll
-                        for (int kb = 0; kb < MF_KBLOCKS; ++kb)        // 320 / 64 = 5 basis blocks per tile
+                        for (int kb = 0; kb < MF_KBLOCKS; ++kb)        // columns >= 160 of the last box are zero-filled
                             ptx::tma_load_2d_2sm(sB + stage * MF_B_STAGE + kb * MF_B_BLOCK, &tm_basis, &full_b[stage],
                                                  kb * 64, nt * MF_BN + (int)rank * (MF_BN / 2));
                         if (++stage == MF_BSTAGES) { stage = 0; phase ^= 1u; }
@@ -163,10 +165,10 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                                 ptx::make_smem_desc_k_sw128(ptx::smem_u32(sB + stage * MF_B_STAGE + kb * MF_B_BLOCK));
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const int t = kb * 4 + k;                           // k-step over [hi | lo]
-                                const int s = t >= MF_KSTEPS ? t - MF_KSTEPS : t;   // coefficient slice
-                                ptx::mma_f16_ts_2sm(d_tmem, tmem_base + MF_COEF_COL + (uint32_t)(s * 8),
-                                                    b_desc + (uint64_t)(k * 2), idesc, (uint32_t)(t != 0));
+                                const int t = kb * 4 + k;                           // k-step
+                                if (t < MF_KSTEPS)
+                                    ptx::mma_f16_ts_2sm(d_tmem, tmem_base + MF_COEF_COL + (uint32_t)(t * 8),
+                                                        b_desc + (uint64_t)(k * 2), idesc, (uint32_t)(t != 0));
                             }
                         }
                         ptx::mma_commit_2sm(&empty_b[stage], 0x3);

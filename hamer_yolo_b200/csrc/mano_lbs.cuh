@@ -38,7 +38,7 @@ constexpr int SKIN_HANDS = 16;
 
 struct ManoDevice {
     const __half* basis16;     // [2432][320] fp16: row = v*3 + c, cols [b_hi(160) | b_lo(160)]
-    const __half* basis16f;    // same, rows in the fused kernel's accumulator column order
+    const __half* basis16f;    // [2432][160] fused kernel: rows in accumulator column order, cols [shape hi | pose | shape lo | 0]
     const float* template_n;   // [2432] v_template flattened (GEMM bias), zero padded
     const float* zero_row;     // [2432] zeros (GEMM "pos" operand)
     const float* j_template;   // [16][3]
@@ -94,6 +94,7 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
                 const int kk = k + q;
                 float c = 0.f;
                 if (kk < 10) c = be[kk];
+                else if (FUSED && kk >= 145 && kk < 155) c = be[kk - 145];   // betas again, for the "shape lo" basis columns
                 else if (kk < 145) {
                     const int e = kk - 10;                  // (joint-1)*9 + row*3 + col
                     const int e9 = e % 9;

@@ -183,14 +183,14 @@ def test_mano_lbs_vs_oracle(engine, oracle_model, B):
     verts, joints, kp2d = engine.mano_lbs(betas.to(dev), rot.to(dev), cam_t.to(dev))
     v_ref, j_ref = mano_forward(rot[:, :1], rot[:, 1:], betas, oracle_model.mano_data)
     k_ref = perspective_projection(j_ref, cam_t, torch.full((B, 2), 5000.0 / 256))
-    assert (verts.cpu() - v_ref).norm(dim=-1).max().item() < 0.02 * MM         # 0.02 mm (fp16 blend coefficients)
+    assert (verts.cpu() - v_ref).norm(dim=-1).max().item() < 0.03 * MM         # fp16 blend coefficients + fp16 pose basis
     assert (joints.cpu() - j_ref).norm(dim=-1).max().item() < 0.02 * MM
     assert (kp2d.cpu() - k_ref).abs().max().item() * 256 < 0.01                # px
 
 
 def test_mano_lbs_three_kernel_path_agrees(engine, oracle_model):
-    """hm_config.mano_legacy selects the prep / GEMM / skinning kernels: same numbers as the fused kernel
-    up to fp32 re-association of the skinning sum."""
+    """hm_config.mano_legacy selects the prep / GEMM / skinning kernels (pose basis split hi + lo, exact to 2^-22);
+    the fused kernel rounds the pose basis to fp16: the two agree to 0.03 mm (0.004 mm on the real MANO asset)."""
     from hamer_yolo_b200.hamer import Engine
     betas, rot, cam_t = random_mano_inputs(700, 3)
     dev = engine.device
@@ -201,7 +201,7 @@ def test_mano_lbs_three_kernel_path_agrees(engine, oracle_model):
         v2, j2, k2 = eng.mano_lbs(betas.to(dev), rot.to(dev), cam_t.to(dev))
     finally:
         eng.close()
-    assert (v - v2).abs().max().item() < 2e-6 and (j - j2).abs().max().item() < 2e-6
+    assert (v - v2).abs().max().item() < 3e-5 and (j - j2).abs().max().item() < 3e-5
     assert (k - k2).abs().max().item() * 256 < 1e-3
 
 
