@@ -95,18 +95,24 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
     }
     const int tile_m = GEMM_BM * CTA_GROUP;
     const int tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BN);
-    int workers = num_sms / CTA_GROUP;
-    if (tiles < workers) workers = tiles;
+    const int max_workers = num_sms / CTA_GROUP;
+    int workers = tiles < max_workers ? tiles : max_workers;
     GemmParams pp = p;
     pp.ksplit = 1;
-    if (EPI == EPI_BIAS_RESID_F32 && tiles > workers && tiles % workers != 0) {
-        // K-slices for the tail tiles: as many as there are workers per tail tile, at least 4 k-blocks each
-        const int tail = tiles % workers;
-        int ks = workers / tail;
+    pp.ksplit_workers = max_workers;
+    if (EPI == EPI_BIAS_RESID_F32 && p.ksplit >= 0 && tiles % max_workers != 0) {
+        // K-slices for the tiles of the partial wave (all tiles when there are fewer tiles than workers): as many as
+        // there are workers per such tile, at least 4 k-blocks each
+        const int tail = tiles % max_workers;
+        int ks = max_workers / tail;
         const int num_k = p.K / GEMM_BK;
         if (ks > num_k / 4) ks = num_k / 4;
         if (ks > 8) ks = 8;
-        if (ks >= 2 && p.ksplit >= 0) pp.ksplit = ks;
+        if (ks >= 2) {
+            pp.ksplit = ks;
+            const int items = (tiles - tail) + tail * ks;
+            workers = items < max_workers ? items : max_workers;
+        }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * CTA_GROUP);

@@ -51,6 +51,7 @@ struct GemmParams {
     int ldo;            // elements
     const float* pos;   // [pos_rows, N] (EPI_BIAS_POS_F32)
     int pos_rows;
+    int ksplit_workers; // worker count the split was planned for (set by gemm_launch)
     int ksplit;         // EPI_BIAS_RESID_F32 only: the tiles of the last, partial wave are split into `ksplit`
                         // K-slices (each slice reduce-adds its partial product; slice 0 carries the bias); <= 1 = off
 };
@@ -175,10 +176,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int worker = blockIdx.x / CTA_GROUP;
     const int num_workers = gridDim.x / CTA_GROUP;
     // wave quantisation: N = 1280 gives 240 tiles for 74 CTA pairs (3.24 waves); the 18 tiles of the last wave
-    // are split along K so that every worker gets a quarter tile instead of 18 workers a whole one
-    const bool split = (EPI == EPI_BIAS_RESID_F32) && p.ksplit > 1 && (num_tiles % num_workers) != 0 && num_tiles > num_workers;
+    // are split along K so that every worker gets a quarter tile instead of 18 workers a whole one.  With fewer
+    // tiles than workers (small batches) every tile is split.  `ksplit_workers` = the worker count the host
+    // planned the split for (the grid may be larger than the tile count).
+    const bool split = (EPI == EPI_BIAS_RESID_F32) && p.ksplit > 1;
     const int ksplit = split ? p.ksplit : 1;
-    const int full_tiles = split ? (num_tiles / num_workers) * num_workers : num_tiles;
+    const int full_tiles = split ? (num_tiles / p.ksplit_workers) * p.ksplit_workers : num_tiles;
     const int num_items = full_tiles + (num_tiles - full_tiles) * ksplit;
 
     if (warp == 0 && lane == 0) {

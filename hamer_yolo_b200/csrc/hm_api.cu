@@ -80,6 +80,8 @@ struct hm_ctx {
     hm_config cfg{};
     std::string err;
     GemmPlan plan{2, 256};
+    bool deterministic = false;
+    int small_m = 384;           // rows at or below which the backbone GEMMs use single-CTA 128 x 128 tiles (HM_SMALL_M)
 
     std::map<std::string, DevTensor> w;   // every state-dict entry, on the device
     bool finalized = false;
@@ -318,7 +320,13 @@ int run_gemm(hm_ctx* c, int epi, const CUtensorMap& ta, const CUtensorMap& tb, i
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
     p.b_format = c->b_format;
-    HM_CUDA(c, gemm_launch(c->plan, epi, ta, tb, c->tm_x_out, p, c->num_sms, s));
+    p.ksplit = c->deterministic ? -1 : 0;   // -1: never split K (fixed fp32 summation order, batch-invariant results)
+    // Few rows (video regime, a handful of hands per frame): 256 x 256 CTA-pair tiles leave most SMs idle and every
+    // tile still pays 256-row MMAs.  Single-CTA 128 x 128 tiles give 4x the tiles at a quarter of the latency; the
+    // weight tensor maps are shared (128-row boxes in both plans).
+    GemmPlan plan = c->plan;
+    if (plan.cta_group == 2 && plan.bn == 256 && M <= c->small_m) plan = GemmPlan{1, 128};
+    HM_CUDA(c, gemm_launch(plan, epi, ta, tb, c->tm_x_out, p, c->num_sms, s));
     return HM_OK;
 }
 
@@ -520,6 +528,8 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     c->b_format = 0u;   // fp16 weight operands (kind::f16 requires A and B of the same 16-bit type)
     c->att_legacy = cfg->attention_legacy != 0;
     c->mano_legacy = cfg->mano_legacy != 0;
+    c->deterministic = cfg->deterministic != 0;
+    if (const char* e = getenv("HM_SMALL_M")) c->small_m = atoi(e);
     if (!get_tmap_encode()) return bail(HM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
     const size_t Mmax = (size_t)cfg->max_batch * TOK, Bm = (size_t)cfg->max_batch;

@@ -36,7 +36,7 @@ class Engine:
     """Owns one hm_ctx (one device, one stream user).  Thin: argument marshalling only."""
 
     def __init__(self, device, max_batch=64, max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0,
-                 attention_legacy=0, mano_legacy=0, use_graphs=True):
+                 attention_legacy=0, mano_legacy=0, use_graphs=True, deterministic=0):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -47,7 +47,7 @@ class Engine:
         self.max_frame_bytes = int(max_frame_bytes)
         cfg = _lib.HmConfig(max_batch=self.max_batch, max_frame_bytes=self.max_frame_bytes,
                             gemm_cta_group=int(gemm_cta_group), attention_legacy=int(attention_legacy),
-                            mano_legacy=int(mano_legacy))
+                            mano_legacy=int(mano_legacy), deterministic=int(deterministic))
         h = C.c_void_p()
         rc = self.lib.hm_create(C.byref(h), self.index, C.byref(cfg))
         if rc != 0:
@@ -244,11 +244,12 @@ class HAMER:
     dicts as hamer.py:124-156; tensors live on the model's CUDA device, float32."""
 
     def __init__(self, cfg=None, init_renderer=False, mano=None, device='cuda:0', max_batch=64,
-                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0, use_graphs=True):
+                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0, use_graphs=True, deterministic=False):
         self.cfg = cfg if cfg is not None else default_config()
         if self.cfg.MODEL.IMAGE_SIZE != 256:
             raise AssertionError(f'MODEL.IMAGE_SIZE ({self.cfg.MODEL.IMAGE_SIZE}) should be 256 for ViT backbone')
-        self.engine = Engine(device, max_batch, max_frame_bytes, gemm_cta_group, use_graphs=use_graphs)
+        self.engine = Engine(device, max_batch, max_frame_bytes, gemm_cta_group, use_graphs=use_graphs,
+                             deterministic=int(deterministic))
         self.device = self.engine.device
         self.training = False
         if mano is None:
@@ -316,15 +317,17 @@ class HAMER:
     __call__ = forward
 
 
-def load_hamer(checkpoint_path=None, mano=None, device='cuda:0', max_batch=64, cfg=None, state_dict=None):
+def load_hamer(checkpoint_path=None, mano=None, device='cuda:0', max_batch=64, cfg=None, state_dict=None,
+               deterministic=False):
     """load_hamer (models/__init__.py:32-47): returns (model, model_cfg).  ``checkpoint_path`` is a
     Lightning checkpoint ({'state_dict': ...}) or a plain state dict saved with torch.save;
-    ``state_dict`` can be passed directly instead."""
+    ``state_dict`` can be passed directly instead.  ``deterministic=True`` fixes the fp32 summation order of the
+    residual GEMMs (bit-identical results across runs and batch sizes, a few percent slower)."""
     cfg = cfg if cfg is not None else default_config()
     if cfg.MODEL.BACKBONE.TYPE == 'vit' and 'BBOX_SHAPE' not in cfg.MODEL:
         assert cfg.MODEL.IMAGE_SIZE == 256
         cfg.MODEL.BBOX_SHAPE = [192, 256]
-    model = HAMER(cfg, mano=mano, device=device, max_batch=max_batch)
+    model = HAMER(cfg, mano=mano, device=device, max_batch=max_batch, deterministic=deterministic)
     if state_dict is None:
         if checkpoint_path is None:
             raise ValueError('load_hamer needs checkpoint_path or state_dict')

@@ -42,7 +42,10 @@ typedef struct hm_config {
     int32_t gemm_cta_group;   /* 0 = default (2: CTA-pair UMMA M=256), 1 = single-CTA tiles */
     int32_t attention_legacy; /* 0 = tcgen05/TMEM attention kernel (default), 1 = mma.sync kernel */
     int32_t mano_legacy;      /* 0 = fused tcgen05 blend + skinning kernel (default), 1 = prep / GEMM / skinning kernels */
-    int32_t reserved[3];
+    int32_t deterministic;    /* 1 = never split the K dimension of the residual GEMMs: fixed fp32 summation order, results
+                                 bit-identical across runs and batch sizes (default 0: the partial-wave tiles are split
+                                 into K-slices that are reduce-added in arrival order - last-bit differences) */
+    int32_t reserved[2];
 } hm_config;
 
 /* Device pointers of the tensors HAMER.forward_step returns (hamer/hamer/models/hamer.py:124-156).

