@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace hm {
 
 constexpr int ATT_T = 192;
@@ -51,6 +53,7 @@ __device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 vit_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                      float scale_log2e) {
+    ptx::pdl_prologue();
     extern __shared__ __align__(16) uint8_t att_smem[];
     __half* sQ = reinterpret_cast<__half*>(att_smem);
     const int h = blockIdx.x, b = blockIdx.y;

@@ -44,6 +44,7 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
     int nt = 0;
     auto tick = [&]() { if constexpr (TIMING) { if (threadIdx.x == 0) tk[nt++] = clock64(); } };
     tick();
+    ptx::griddep_launch_dependents();   // PDL: the next kernel may start its launch / set-up
     extern __shared__ uint8_t at5_smem_raw[];
     const uint32_t raw = ptx::smem_u32(at5_smem_raw);
     uint8_t* smem = at5_smem_raw + ((1024u - (raw & 1023u)) & 1023u);    // 128B-swizzled tiles: 1 KB aligned
@@ -66,6 +67,7 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&tm128);
         ptx::prefetch_tmap(&tm32);
+        ptx::griddep_wait();            // qkv comes from the previous kernel; everything below depends on these loads
         ptx::mbar_arrive_expect_tx(&bar[2], AT5_DATA);
         const int row0 = b * AT5_T, col = h * AT5_D;
         for (int m = 0; m < 3; ++m) {                                    // Q, K, V column blocks of qkv

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace hm {
 
 struct CropParams {
@@ -35,6 +37,7 @@ __global__ void __launch_bounds__(256)
 crop_warp_normalize_kernel(const uint8_t* __restrict__ frame, int H, int W, int64_t row_stride,
                            const CropParams* __restrict__ params, const float* __restrict__ lut,
                            float* __restrict__ out) {
+    ptx::pdl_prologue();
     const int n = blockIdx.y, y = blockIdx.x, x = threadIdx.x;
     const CropParams p = params[n];
     const int adelta = cv_round_scaled(__dmul_rn(p.m[0], (double)x));

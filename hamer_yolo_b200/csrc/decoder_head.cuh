@@ -65,6 +65,7 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
 template <int EPI>
 __global__ void __launch_bounds__(SK_COLS * 32)
 skinny_linear_kernel(const SkinnyParams p) {
+    ptx::pdl_prologue();
     extern __shared__ __align__(16) float sk_xs[];              // [SK_ROWS][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * SK_COLS + warp;
@@ -131,6 +132,7 @@ skinny_linear_kernel(const SkinnyParams p) {
 __global__ void __launch_bounds__(256)
 head_scores_kernel(const float* __restrict__ feats, const float* __restrict__ u,
                    float* __restrict__ sc) {
+    ptx::pdl_prologue();
     __shared__ __align__(16) float us[8][1280];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float4* ub = reinterpret_cast<const float4*>(u + (size_t)b * 8 * 1280);
@@ -175,6 +177,7 @@ head_scores_kernel(const float* __restrict__ feats, const float* __restrict__ u,
 __global__ void __launch_bounds__(128)
 head_pool_kernel(const float* __restrict__ feats, const float* __restrict__ sc,
                  float* __restrict__ pooled) {
+    ptx::pdl_prologue();
     __shared__ __align__(16) float a[192][8];          // [token][head]: two float4 broadcasts per token
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int h = warp; h < 8; h += 4) {               // each warp normalises two heads
@@ -210,6 +213,7 @@ head_pool_kernel(const float* __restrict__ feats, const float* __restrict__ sc,
 
 // Broadcast the constant layer-0 token (to_token_embedding.bias + pos_embedding) to every crop.
 __global__ void head_init_token_kernel(const float* __restrict__ tok0, float* __restrict__ x, int B) {
+    ptx::pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * 1024) x[i] = tok0[i & 1023];
 }
@@ -231,6 +235,7 @@ struct HeadOut {
 
 __global__ void head_finalize_kernel(const float* __restrict__ raw, HeadOut o, int B,
                                      float focal, float image_size) {
+    ptx::pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 16) return;
     const int b = i >> 4, j = i & 15;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace hm {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -28,6 +30,7 @@ template <int V, typename OutT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, OutT* __restrict__ y, int rows, float eps) {
+    ptx::pdl_prologue();
     constexpr int D = 128 * V;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -82,6 +85,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_patch16_kernel(const float* __restrict__ img, __half* __restrict__ out, int B) {
+    ptx::pdl_prologue();
     const int b = blockIdx.y, i = blockIdx.x;           // i: 0..15 patch row
     const float* src = img + (size_t)b * 3 * 256 * 256;
     // 3 channels x 16 rows x 192 slice columns = 9216 source pixels; thread handles pairs along x

@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "gemm_tcgen05.cuh"
 
@@ -75,6 +77,29 @@ inline bool make_tmap_attn(CUtensorMap* t128, CUtensorMap* t32, const void* base
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Kernel launch, optionally with the programmatic-stream-serialization attribute (PDL): the launch and set-up of
+// kernel n + 1 then overlap the tail of kernel n (every kernel waits on griddepcontrol.wait before touching
+// dependent memory).  Measured inside the replayed CUDA graph: 1-2.5 % at 1-8 crops, nothing at 64
+// (profiles/r01_notes.md), so it is opt-in: HM_PDL=1.
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("HM_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 struct GemmPlan {
     int cta_group;  // 1 or 2
     int bn;         // 128 or 256
@@ -119,13 +144,15 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CTA_GROUP;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, pp);
 }
 

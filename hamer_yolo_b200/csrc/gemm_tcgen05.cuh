@@ -146,6 +146,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     using Cfg = GemmCfg<CTA_GROUP, BN, EPI>;
     constexpr int STAGES = Cfg::STAGES;
+    ptx::griddep_launch_dependents();   // the next kernel may start its launch / set-up (PDL)
 
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment. The dynamic-smem base offset is identical in
@@ -205,6 +206,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if constexpr (CTA_GROUP == 2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();                // barriers / TMEM / tensor maps are set up; now wait for the previous kernel's data
 
     if (warp == 0) {
         // ===================== TMA producer =====================

@@ -296,7 +296,7 @@ void invert_affine(const double M[6], double out[6]) {
 template <int V, typename OutT>
 void launch_ln(const float* x, const float* g, const float* b, OutT* y, int rows, float eps,
                cudaStream_t s) {
-    layernorm_kernel<V, OutT><<<(rows + 7) / 8, 256, 0, s>>>(x, g, b, y, rows, eps);
+    launch_pdl(layernorm_kernel<V, OutT>, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, y, rows, eps);
 }
 
 cudaError_t launch_skinny(int epi, const float* X, int ldx, long long x_bs, const float* W,
@@ -309,9 +309,9 @@ cudaError_t launch_skinny(int epi, const float* X, int ldx, long long x_bs, cons
     if (K % 64 != 0 || K > SK_KMAX || ldx % 4 != 0) return cudaErrorInvalidValue;
     dim3 grid((N + SK_COLS - 1) / SK_COLS, (B + SK_ROWS - 1) / SK_ROWS, batch);
     const size_t smem = (size_t)SK_ROWS * K * sizeof(float);
-    if (epi == SK_NONE) skinny_linear_kernel<SK_NONE><<<grid, SK_COLS * 32, smem, s>>>(p);
-    else if (epi == SK_GELU) skinny_linear_kernel<SK_GELU><<<grid, SK_COLS * 32, smem, s>>>(p);
-    else skinny_linear_kernel<SK_RESID><<<grid, SK_COLS * 32, smem, s>>>(p);
+    if (epi == SK_NONE) launch_pdl(skinny_linear_kernel<SK_NONE>, dim3(grid), dim3(SK_COLS * 32), smem, s, p);
+    else if (epi == SK_GELU) launch_pdl(skinny_linear_kernel<SK_GELU>, dim3(grid), dim3(SK_COLS * 32), smem, s, p);
+    else launch_pdl(skinny_linear_kernel<SK_RESID>, dim3(grid), dim3(SK_COLS * 32), smem, s, p);
     return cudaGetLastError();
 }
 
@@ -334,7 +334,7 @@ int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStre
     const int M = B * TOK;
     const float att_scale = 0.11180339887498948f * 1.4426950408889634f;   // 80^-0.5 * log2(e)
     int rc;
-    { ProfScope ps(c, s, PC_IM2COL); im2col_patch16_kernel<<<dim3(16, B), 256, 0, s>>>(img, c->patches, B); }
+    { ProfScope ps(c, s, PC_IM2COL); launch_pdl(im2col_patch16_kernel, dim3(16, B), dim3(256), 0, s, img, c->patches, B); }
     { ProfScope ps(c, s, PC_GEMM_PATCH);
       if ((rc = run_gemm(c, EPI_BIAS_POS_F32, c->tm_patches, c->tm_wpatch, M, DM, KPATCH, c->b_patch, c->x, c->pos_tab, s))) return rc; }
     for (int i = 0; i < DEPTH; ++i) {
@@ -343,9 +343,9 @@ int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStre
         { ProfScope ps(c, s, PC_GEMM_QKV);
           if ((rc = run_gemm(c, EPI_BIAS_BF16, c->tm_xn, w.tm_qkv, M, 3 * DM, DM, w.b_qkv, c->qkv, nullptr, s))) return rc; }
         { ProfScope ps(c, s, PC_ATTENTION);
-          if (c->att_legacy) vit_attention_kernel<<<dim3(16, B), ATT_THREADS, ATT_SMEM_BYTES, s>>>(c->qkv, c->att, att_scale);
-          else vit_attention_tc5_kernel<false><<<dim3(16, B), AT5_THREADS, AT5_SMEM_BYTES, s>>>(
-                   c->tm_att128, c->tm_att32, c->att, att_scale, nullptr); }
+          if (c->att_legacy) launch_pdl(vit_attention_kernel, dim3(16, B), dim3(ATT_THREADS), ATT_SMEM_BYTES, s, c->qkv, c->att, att_scale);
+          else launch_pdl(vit_attention_tc5_kernel<false>, dim3(16, B), dim3(AT5_THREADS), AT5_SMEM_BYTES, s,
+                          c->tm_att128, c->tm_att32, c->att, att_scale, nullptr); }
         { ProfScope ps(c, s, PC_GEMM_PROJ);
           if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_att, w.tm_proj, M, DM, DM, w.b_proj, c->x, nullptr, s))) return rc; }
         { ProfScope ps(c, s, PC_LAYERNORM); launch_ln<10, __half>(c->x, w.ln2_g, w.ln2_b, c->xn, M, 1e-6f, s); }
@@ -361,7 +361,7 @@ int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStre
 
 int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaStream_t s) {
     ProfScope ps(c, s, PC_HEAD);
-    head_init_token_kernel<<<(B * HD + 255) / 256, 256, 0, s>>>(c->tok0, c->hx, B);
+    launch_pdl(head_init_token_kernel, dim3((B * HD + 255) / 256), dim3(256), 0, s, c->tok0, c->hx, B);
     const float scale = 0.125f;   // dim_head ** -0.5 = 64^-0.5
     for (int l = 0; l < HDEPTH; ++l) {
         const HeadLayerW& w = c->hl[l];
@@ -375,8 +375,8 @@ int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaS
         // u[b,h,:] = scale * W_k,h^T q[b,h,:]
         HM_CUDA(c, launch_skinny(SK_NONE, c->hq, 512, 64, w.w_kT, (long long)DM * 64, nullptr, 0,
                                  c->hu, 8 * DM, DM, B, DM, 64, 8, scale, s));
-        head_scores_kernel<<<dim3(6, B), 256, 0, s>>>(feats, c->hu, c->hsc);
-        head_pool_kernel<<<dim3(10, B), 128, 0, s>>>(feats, c->hsc, c->hpool);
+        launch_pdl(head_scores_kernel, dim3(6, B), dim3(256), 0, s, feats, c->hu, c->hsc);
+        launch_pdl(head_pool_kernel, dim3(10, B), dim3(128), 0, s, feats, c->hsc, c->hpool);
         // o[b, h*64 + d] = W_v,h pooled[b,h,:]
         HM_CUDA(c, launch_skinny(SK_NONE, c->hpool, 8 * DM, DM, w.w_v, (long long)64 * DM, nullptr, 0,
                                  c->ho, 512, 64, B, 64, DM, 8, 1.f, s));
@@ -398,7 +398,7 @@ int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaS
     ho.pred_cam_t = c->hcamt;
     ho.focal_length = out && out->focal_length ? out->focal_length : scratch + (size_t)B * 147;
     ho.rotmats = c->hrot;
-    head_finalize_kernel<<<(B * 16 + 127) / 128, 128, 0, s>>>(c->hraw, ho, B, 5000.0f, 256.0f);
+    launch_pdl(head_finalize_kernel, dim3((B * 16 + 127) / 128), dim3(128), 0, s, c->hraw, ho, B, 5000.0f, 256.0f);
     HM_CUDA(c, cudaGetLastError());
     if (out && out->betas)
         HM_CUDA(c, cudaMemcpyAsync(out->betas, c->hbetas, (size_t)B * 10 * 4, cudaMemcpyDeviceToDevice, s));
@@ -432,7 +432,7 @@ int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const fl
         pa.kp2d = proj ? kp2d + (size_t)lo * 42 : nullptr;
         pa.cam_t = proj ? cam_t + (size_t)lo * 3 : nullptr;
         pa.focal_over_size = 5000.0f / 256.0f;
-        mano_prep_kernel<true><<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
+        launch_pdl(mano_prep_kernel<true>, dim3((n + 7) / 8), dim3(128), 0, s, c->mano, pa);
         ManoFusedArgs a{};
         a.coef = c->mf_coef; a.Au = c->mf_Au; a.cam_t = pa.cam_t; a.verts = verts + (size_t)lo * MANO_V * 3;
         a.joints = pa.joints; a.kp2d = pa.kp2d; a.focal_over_size = pa.focal_over_size; a.B = n;
@@ -447,11 +447,13 @@ int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const fl
         cfg.blockDim = dim3(MF_THREADS);
         cfg.dynamicSmemBytes = MF_SMEM_BYTES;
         cfg.stream = s;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         HM_CUDA(c, cudaLaunchKernelEx(&cfg, mano_fused_kernel, c->tm_fbasis, c->mano, a));
     }
     HM_CUDA(c, cudaGetLastError());
@@ -469,7 +471,7 @@ int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* c
         ManoPrepArgs pa{};
         pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
         pa.coef = c->m_coef; pa.A = c->m_A; pa.jpos = c->m_jpos; pa.B = n;
-        mano_prep_kernel<false><<<(n + 7) / 8, 128, 0, s>>>(c->mano, pa);
+        launch_pdl(mano_prep_kernel<false>, dim3((n + 7) / 8), dim3(128), 0, s, c->mano, pa);
         GemmParams p{};
         p.M = n; p.N = MANO_NPAD; p.K = MANO_KTOT; p.bias = c->mano.template_n; p.out = c->m_vposed;
         p.ldo = MANO_NPAD; p.pos = c->mano.zero_row; p.pos_rows = 1; p.b_format = 0;
@@ -482,7 +484,7 @@ int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* c
         a.kp2d = (cam_t != nullptr && kp2d != nullptr) ? kp2d + (size_t)lo * 42 : nullptr;
         a.focal_over_size = 5000.0f / 256.0f;
         a.B = n;
-        mano_skin_kernel<<<(n + SKIN_HANDS - 1) / SKIN_HANDS, MANO_VTHREADS, sizeof(SkinSmem), s>>>(c->mano, a);
+        launch_pdl(mano_skin_kernel, dim3((n + SKIN_HANDS - 1) / SKIN_HANDS), dim3(MANO_VTHREADS), sizeof(SkinSmem), s, c->mano, a);
     }
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
@@ -979,11 +981,14 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
         HM_CUDA(c, cudaEventSynchronize(c->crop_event));
         c->crop_event_pending = false;
     }
+    double band_lo = (double)H, band_hi = -1.0;   // source rows any crop can read (host frames: only these are uploaded)
     for (int i = 0; i < n; ++i) {
         const double* box = boxes_xyxy + 4 * i;
         if (!(box[2] > box[0]) || !(box[3] > box[1])) return fail(c, HM_ERR_INVALID, "hm_preprocess: empty box");
         double cx, cy, size, M[6];
         box_to_affine(box, &cx, &cy, &size, M);
+        if (cy - 0.5 * size < band_lo) band_lo = cy - 0.5 * size;
+        if (cy + 0.5 * size > band_hi) band_hi = cy + 0.5 * size;
         invert_affine(M, c->crop_host[i].m);
         c->crop_host[i].flip = is_right[i] ? 0 : 1;
         c->crop_host[i].pad = 0;
@@ -996,7 +1001,14 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
         const size_t bytes = (size_t)H * (size_t)row_stride;
         if (!c->frame_dev || bytes > (size_t)c->cfg.max_frame_bytes)
             return fail(c, HM_ERR_INVALID, "hm_preprocess: frame larger than hm_config.max_frame_bytes");
-        HM_CUDA(c, cudaMemcpyAsync(c->frame_dev, frame_bgr, bytes, cudaMemcpyHostToDevice, s));
+        // the warp maps the 256 x 256 patch onto the square [c - size/2, c + size/2]^2 (no rotation) and reads
+        // bilinear neighbours: rows outside the union of those windows (+ margin) are never touched
+        long r0 = (long)floor(band_lo) - 4, r1 = (long)ceil(band_hi) + 4;
+        if (r0 < 0) r0 = 0;
+        if (r1 > H - 1) r1 = H - 1;
+        if (r1 >= r0)
+            HM_CUDA(c, cudaMemcpyAsync(c->frame_dev + (size_t)r0 * row_stride, frame_bgr + (size_t)r0 * row_stride,
+                                       (size_t)(r1 - r0 + 1) * row_stride, cudaMemcpyHostToDevice, s));
         frame = c->frame_dev;
     }
     HM_CUDA(c, cudaMemcpyAsync(c->crop_dev, c->crop_host, (size_t)n * sizeof(CropParams), cudaMemcpyHostToDevice, s));
@@ -1004,7 +1016,7 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
     c->crop_event_pending = true;
     {
         ProfScope ps(c, s, PC_CROP);
-        crop_warp_normalize_kernel<<<dim3(256, n), 256, 0, s>>>(frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
+        launch_pdl(crop_warp_normalize_kernel, dim3(256, n), dim3(256), 0, s, frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
     }
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
@@ -1125,10 +1137,10 @@ int hm_test_attention(hm_ctx* c, int variant, const uint16_t* qkv, uint16_t* out
             return fail(c, HM_ERR_CUDA, "hm_test_attention: tensor map encoding failed");
         __half* o = reinterpret_cast<__half*>(out);
         if (variant == 1)
-            vit_attention_tc5_kernel<false><<<dim3(16, B), AT5_THREADS, AT5_SMEM_BYTES, s>>>(t128, t32, o, sc, nullptr);
+            launch_pdl(vit_attention_tc5_kernel<false>, dim3(16, B), dim3(AT5_THREADS), AT5_SMEM_BYTES, s, t128, t32, o, sc, nullptr);
         else {
             long long* dbg = reinterpret_cast<long long*>(c->hbuf);
-            vit_attention_tc5_kernel<true><<<dim3(16, B), AT5_THREADS, AT5_SMEM_BYTES, s>>>(t128, t32, o, sc, dbg);
+            launch_pdl(vit_attention_tc5_kernel<true>, dim3(16, B), dim3(AT5_THREADS), AT5_SMEM_BYTES, s, t128, t32, o, sc, dbg);
             HM_CUDA(c, cudaMemcpyAsync(out, c->hbuf, (size_t)16 * B * 16 * sizeof(long long), cudaMemcpyDeviceToDevice, s));
         }
     }

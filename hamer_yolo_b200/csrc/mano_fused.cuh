@@ -106,6 +106,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
     const int worker = blockIdx.x >> 1, num_workers = gridDim.x >> 1;
     const int pair_tiles = (a.B + 2 * MF_BM - 1) / (2 * MF_BM);
     const int units = pair_tiles * a.n_split;
+    ptx::griddep_launch_dependents();   // PDL: the next kernel may start its launch / set-up
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tm_basis);
@@ -119,6 +120,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
     ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();                // coefficients / transforms come from the prep kernel
 
     // Register re-balancing between warpgroups: the single-lane roles give registers back, the
     // skinning warps take them.

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace hm {
 
 constexpr int MANO_V = 778;
@@ -75,6 +77,7 @@ struct ManoPrepArgs {
 template <bool FUSED>
 __global__ void __launch_bounds__(128)
 mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
+    ptx::pdl_prologue();
     __shared__ float sJ[8][MANO_J][3];
     __shared__ float sG[8][MANO_J][12];
     const int slot = threadIdx.x >> 4, j = threadIdx.x & 15;
@@ -199,6 +202,7 @@ struct SkinSmem {
 
 __global__ void __launch_bounds__(MANO_VTHREADS, 1)
 mano_skin_kernel(const ManoDevice m, const ManoSkinArgs a) {
+    ptx::pdl_prologue();
     extern __shared__ __align__(16) uint8_t skin_smem_raw[];
     SkinSmem& S = *reinterpret_cast<SkinSmem*>(skin_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5;

@@ -26,6 +26,23 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+// ----------------------------------------------------------------------------------------------
+// Every kernel of the hot path calls pdl_prologue() first: it lets the next kernel of the stream start its own
+// launch + set-up while this grid is still running, then waits until the previous grid has completed and its
+// memory is visible.  Nothing before the wait touches global memory that another kernel writes.
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_prologue() {
+    griddep_launch_dependents();
+    griddep_wait();
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
