@@ -54,7 +54,9 @@ constexpr uint32_t MF_B_STAGE = MF_KBLOCKS * MF_B_BLOCK;      // 18 KB per CTA p
 constexpr uint32_t MF_WARP_STAGE = 32 * MF_GCOLS * 4;         // 3,072 B per epilogue warp: 32 dense rows of 24 floats
 constexpr uint32_t MF_STAGING = MF_EPI_WARPS * MF_WARP_STAGE;
 constexpr uint32_t MF_OFF_STAGING = MF_BSTAGES * MF_B_STAGE;
-constexpr uint32_t MF_OFF_BARS = MF_OFF_STAGING + MF_STAGING;
+constexpr uint32_t MF_TAB_BYTES = 98 * 48 * 16;                // group tables of the 98 live 8-vertex groups, resident for the whole kernel
+constexpr uint32_t MF_OFF_TAB = MF_OFF_STAGING + MF_STAGING;
+constexpr uint32_t MF_OFF_BARS = MF_OFF_TAB + MF_TAB_BYTES;
 constexpr uint32_t MF_SMEM_BYTES = 1024 + MF_OFF_BARS + 256;
 constexpr uint32_t MF_TMEM_COLS = 512;
 constexpr uint32_t MF_AU_COL = 2 * MF_BN;                     // transforms: joint j at MF_AU_COL + 12 j
@@ -66,7 +68,6 @@ constexpr uint32_t MF_COEF_COL = MF_AU_COL + MANO_J * 12;     // coefficients: k
 //   float  [64,192) weights [16 slots][8 vertices]
 constexpr int MF_TAB_F4 = 48;
 static_assert(MF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(MF_TAB_F4 * 16 <= MF_WARP_STAGE, "the group table lives in the warp's staging buffer");
 static_assert(MF_COEF_COL + MANO_KB / 2 <= MF_TMEM_COLS, "tensor memory budget");
 // setmaxnreg moves registers inside the CTA's launch allocation only (640 threads x 96 registers): the
 // re-balanced total must fit or the .inc blocks forever
@@ -92,6 +93,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
     uint8_t* smem = mf_smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* sB = smem;
     uint8_t* sStage = smem + MF_OFF_STAGING;
+    uint8_t* sTab = smem + MF_OFF_TAB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MF_OFF_BARS);
     uint64_t* full_b = bars;                       // [MF_BSTAGES] basis tile landed (leader's)
     uint64_t* empty_b = bars + MF_BSTAGES;         // [MF_BSTAGES] MMAs that read the tile retired (both CTAs)
@@ -188,7 +190,8 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
         const int ew = warp - 4, quad = warp & 3, part = ew >> 2;
         const int hl = quad * 32 + lane;                                   // hand inside this CTA's tile = TMEM lane
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t sbase = ptx::smem_u32(sStage) + (uint32_t)ew * MF_WARP_STAGE;   // group table, then the output tile
+        const uint32_t sbase = ptx::smem_u32(sStage) + (uint32_t)ew * MF_WARP_STAGE;   // this warp's output tile
+        const uint32_t tab0 = ptx::smem_u32(sTab);                                      // + 768 * group
         // staging layout: row = lane (96 dense bytes), pair k of the row at position (k + rot) mod 12
         const int rot = 3 * ((lane >> 2) & 3);
         const uint32_t wbase = sbase + (uint32_t)lane * (MF_GCOLS * 4) + 8 * rot;
@@ -206,9 +209,12 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                 goff[kk][par] = r * (MANO_V * 3) + 2 * ((pos - rr + 12) % 12);
             }
         }
+        // the constant group tables (template, joint unions, pair masks, weights; 74 KB) are loaded once: a per-tile
+        // global load sat on the critical path of every tile while the L2 absorbs the kernel's 2 TB/s of stores
+        for (int i = (int)threadIdx.x - 128; i < (int)(MF_TAB_BYTES / 16); i += 32 * MF_EPI_WARPS)
+            ptx::sts128(tab0 + 16 * i, __ldg(m.fz_tab + i));
         int acc = 0;
         uint32_t acc_phase = 0;
-        float4 tb0, tb1;                                                    // this lane's slice of the next group's table
         for (int unit = worker; unit < units; unit += num_workers) {
             const int pt = unit / a.n_split, q = unit - pt * a.n_split;
             const int nt0 = q * MF_NT / a.n_split, nt1 = (q + 1) * MF_NT / a.n_split;
@@ -237,10 +243,6 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                     const uint4 f = __ldg(csrc + 4);
                     c4[0] = f.x; c4[1] = f.y; c4[2] = f.z; c4[3] = f.w;
                 }
-                {
-                    const float4* t = m.fz_tab + (size_t)(nt0 * MF_PARTS + part) * MF_TAB_F4;
-                    tb0 = __ldg(t + lane); tb1 = __ldg(t + 32 + (lane & 15));
-                }
                 // every epilogue warp has consumed the previous unit's last accumulator (so its MMAs, the readers
                 // of the coefficients, have retired) and is done with the previous transforms
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * MF_EPI_WARPS) : "memory");
@@ -252,8 +254,6 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                 ptx::tmem_st_wait();
             }
             ptx::tc_fence_before();
-            ptx::sts128(sbase + lane * 16, tb0);
-            if (lane < 16) ptx::sts128(sbase + 512 + lane * 16, tb1);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(coef_full, 0);          // 32 warps of the pair -> the MMA issuer may start
             asm volatile("bar.sync 1, %0;" ::"n"(32 * MF_EPI_WARPS) : "memory");
@@ -262,10 +262,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
             for (int nt = nt0; nt < nt1; ++nt) {
                 const int g = nt * MF_PARTS + part;                        // 8-vertex group
                 const bool active = g * MF_GCOLS < MANO_V * 3 && !(a.dbg & 4);   // the last two groups are padding (warp-uniform)
-                if (nt + 1 < nt1) {                                        // L2 latency hidden behind this tile's arithmetic
-                    const float4* t = m.fz_tab + (size_t)(g + MF_PARTS) * MF_TAB_F4;
-                    tb0 = __ldg(t + lane); tb1 = __ldg(t + 32 + (lane & 15));
-                }
+                const uint32_t tab = tab0 + (uint32_t)g * (MF_TAB_F4 * 16);  // this group's table (groups >= 98 are padding, never read)
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
                 const uint32_t t_addr = tmem_lane + (uint32_t)(acc * MF_BN + part * MF_GCOLS);
@@ -284,7 +281,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                     float2 P[4][3], O[4][3];
 #pragma unroll
                     for (int j4 = 0; j4 < 6; ++j4) {
-                        const float4 t4 = ptx::lds128(sbase + j4 * 16);
+                        const float4 t4 = ptx::lds128(tab + j4 * 16);
                         const uint32_t* r = j4 < 4 ? &ra[j4 * 4] : &rb[(j4 - 4) * 4];
                         P[(j4 * 2) / 3][(j4 * 2) % 3] =
                             __fadd2_rn(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(t4.x, t4.y));
@@ -295,15 +292,15 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) O[i][c] = make_float2(0.f, 0.f);
-                    const int nu = (a.dbg & 2) ? 0 : (int)ptx::lds32(sbase + 96);
-                    const uint32_t tipmask = ptx::lds32(sbase + 100);
+                    const int nu = (a.dbg & 2) ? 0 : (int)ptx::lds32(tab + 96);
+                    const uint32_t tipmask = ptx::lds32(tab + 100);
                     for (int u = 0; u < nu; ++u) {
-                        const uint32_t jp = ptx::lds32(sbase + 128 + u * 4);
+                        const uint32_t jp = ptx::lds32(tab + 128 + u * 4);
                         const uint32_t pm = jp >> 16;                       // vertex pairs with a non-zero weight
                         uint32_t ta[8], tc[4];
                         ptx::tmem_ld_32x8(tmem_lane + MF_AU_COL + (jp & 0xffffu), ta);
                         ptx::tmem_ld_32x4(tmem_lane + MF_AU_COL + (jp & 0xffffu) + 8, tc);
-                        const float4 W0 = ptx::lds128(sbase + 256 + u * 32), W1 = ptx::lds128(sbase + 272 + u * 32);
+                        const float4 W0 = ptx::lds128(tab + 256 + u * 32), W1 = ptx::lds128(tab + 272 + u * 32);
                         ptx::tmem_ld_wait();
                         const float4 Rc[3] = {
                             make_float4(__uint_as_float(ta[0]), __uint_as_float(ta[1]), __uint_as_float(ta[2]), __uint_as_float(ta[3])),
@@ -325,7 +322,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                         }
                     }
                     // ---- transpose through shared memory: lane = hand  ->  lane = 8 contiguous bytes ----
-                    __syncwarp();                                           // every lane is done with the group table
+                    __syncwarp();                                           // the previous tile's read-out of the staging rows is done
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         // natural order of the row: pair 3i = (x0 y0), 3i+1 = (z0 x1), 3i+2 = (y1 z1)
@@ -382,14 +379,7 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const ManoDevice
                         }
                     }
                 }
-                if (nt + 1 < nt1) {                                         // next group's table replaces the output tile
-                    __syncwarp();
-                    ptx::sts128(sbase + lane * 16, tb0);
-                    if (lane < 16) ptx::sts128(sbase + 512 + lane * 16, tb1);
-                    __syncwarp();
-                }
             }
-            __syncwarp();                                                   // the next unit's table store overwrites the tile
         }
     }
 
