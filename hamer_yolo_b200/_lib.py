@@ -32,7 +32,7 @@ class HmError(RuntimeError):
 # every symbol include/hamer_b200.h declares (tests check the library exports all of them)
 EXPORTS = ('hm_create', 'hm_destroy', 'hm_last_error', 'hm_set_weight', 'hm_finalize_weights',
            'hm_set_mano', 'hm_preprocess', 'hm_forward', 'hm_backbone', 'hm_mano_head',
-           'hm_mano_lbs', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
+           'hm_mano_lbs', 'hm_camera_postprocess', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
            'hm_profile_collect', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention')
 
 PROFILE_CATEGORIES = ('im2col', 'gemm_patch', 'layernorm', 'gemm_qkv', 'attention', 'gemm_proj',
@@ -64,6 +64,7 @@ def load():
     lib.hm_backbone.argtypes = [vp, vp, i32, vp, vp]
     lib.hm_mano_head.argtypes = [vp, vp, i32, C.POINTER(HmOutputs), vp]
     lib.hm_mano_lbs.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.hm_camera_postprocess.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.hm_forward_launch_count.argtypes = [vp]
     lib.hm_version.argtypes = []
     lib.hm_version.restype = C.c_char_p

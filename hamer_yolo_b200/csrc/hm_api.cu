@@ -1046,6 +1046,56 @@ int hm_profile_collect(hm_ctx* c, double* ms_per_cat, int32_t* spans_per_cat, in
     return HM_OK;
 }
 
+// Camera post-processing of estimate_from_rgb (infer.py:382-528 -> utils/renderer.py:24-74 cam_crop_to_full and the
+// full-image projection), one thread per (hand, keypoint).  Every operation is a separately rounded fp32 op in the
+// reference's order, so the result is bit-identical to the PyTorch expressions.
+__global__ void camera_postprocess_kernel(const float* __restrict__ pred_cam, float* __restrict__ kp3d,
+                                          const float* __restrict__ meta, int meta_stride, int fxfy_differ,
+                                          int add_center, int n, float* __restrict__ cam_t_full,
+                                          float* __restrict__ kp2d_full) {
+    ptx::pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = i / 21, k = i - h * 21;
+    if (h >= n) return;
+    const float* mt = meta + (size_t)h * meta_stride;
+    const float flip = mt[5], fx = mt[12], fy = mt[13], cx = mt[14], cy = mt[15];
+    const float c0 = pred_cam[h * 3], c1 = __fmul_rn(pred_cam[h * 3 + 1], __fsub_rn(1.0f, __fmul_rn(2.0f, flip))),
+                c2 = pred_cam[h * 3 + 2];
+    const float bs = __fadd_rn(__fmul_rn(mt[2], c0), 1e-9f);
+    const float tz = __fdiv_rn(__fmul_rn(2.0f, fx), bs);
+    const float tx = __fadd_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(mt[0], cx)), bs), c1);
+    float ty = __fadd_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(mt[1], cy)), bs), c2);
+    if (fxfy_differ) ty = __fmul_rn(ty, __fdiv_rn(fx, fy));
+    if (k == 0) { cam_t_full[h * 3] = tx; cam_t_full[h * 3 + 1] = ty; cam_t_full[h * 3 + 2] = tz; }
+    float* p = kp3d + ((size_t)h * 21 + k) * 3;
+    const float x = __fmul_rn(p[0], flip), y = p[1], z = p[2];
+    p[0] = x;                                                                   // infer.py:392 (in place)
+    const float X = __fadd_rn(x, tx), Y = __fadd_rn(y, ty), Z = __fadd_rn(z, tz);
+    float u, v;
+    if (add_center) {                                                           // intrinsics given (infer.py:474-486)
+        const float depth = __fadd_rn(Z, 1e-9f);
+        u = __fadd_rn(__fmul_rn(__fdiv_rn(X, depth), fx), cx);
+        v = __fadd_rn(__fmul_rn(__fdiv_rn(Y, depth), fy), cy);
+    } else {                                                                    // perspective_projection, zero centre
+        u = __fmul_rn(__fdiv_rn(X, Z), fx);
+        v = __fmul_rn(__fdiv_rn(Y, Z), fy);
+    }
+    kp2d_full[((size_t)h * 21 + k) * 2] = u;
+    kp2d_full[((size_t)h * 21 + k) * 2 + 1] = v;
+}
+
+int hm_camera_postprocess(hm_ctx* c, const float* pred_cam, float* kp3d, const float* meta, int meta_stride,
+                          int fxfy_differ, int add_center, int n, float* cam_t_full, float* kp2d_full, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!pred_cam || !kp3d || !meta || !cam_t_full || !kp2d_full || n <= 0 || meta_stride < 16)
+        return fail(c, HM_ERR_INVALID, "hm_camera_postprocess: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    HM_CUDA(c, launch_pdl(camera_postprocess_kernel, dim3((n * 21 + 127) / 128), dim3(128), 0, s, pred_cam, kp3d, meta,
+                          meta_stride, fxfy_differ, add_center, n, cam_t_full, kp2d_full));
+    return HM_OK;
+}
+
 int hm_backbone(hm_ctx* c, const float* img, int B, float* feats, void* stream) {
     int rc = check_ready(c, B, true, false);
     if (rc) return rc;

@@ -223,6 +223,19 @@ class Engine:
                 C.c_void_p(size.ctypes.data), C.c_void_p(trans.ctypes.data), self.stream()))
         return img, center, size, trans
 
+    def camera_postprocess(self, pred_cam, kp3d, meta, fxfy_differ, add_center):
+        """meta: CUDA float32 [n, >=16] (layout: include/hamer_b200.h).  kp3d is flipped in place.
+        Returns (cam_t_full [n,3], kp2d_full [n,21,2])."""
+        n = pred_cam.shape[0]
+        assert meta.is_cuda and meta.dtype == torch.float32 and meta.stride(1) == 1 and kp3d.is_contiguous()
+        cam_t = torch.empty(n, 3, device=self.device, dtype=torch.float32)
+        kp2d = torch.empty(n, 21, 2, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.hm_camera_postprocess(
+                self.h, _ptr(pred_cam.contiguous()), _ptr(kp3d), _ptr(meta), int(meta.stride(0)), int(bool(fxfy_differ)),
+                int(bool(add_center)), n, _ptr(cam_t), _ptr(kp2d), self.stream()))
+        return cam_t, kp2d
+
     def launch_count(self):
         return int(self.lib.hm_forward_launch_count(self.h))
 

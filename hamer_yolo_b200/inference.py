@@ -41,6 +41,34 @@ def custom_cam_crop_to_full(cam_bbox, box_center, box_size, img_size, fx, fy, cx
     return torch.stack([tx, ty, tz], dim=-1)
 
 
+META_COLS = 16
+
+
+class _Batch(dict):
+    """The dict prepare_batch_bbox returns.  The small per-hand tensors ('box_center', 'box_size', 'img_size',
+    'do_flip', 'trans', 'inv_trans') are views of one device tensor that is uploaded once by meta_dev()
+    (estimate_from_rgb adds the intrinsics to the same upload before calling it)."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self._meta_host = None
+        self._meta_dev = None
+        self._dev = None
+
+    def meta_dev(self):
+        if self._meta_dev is None:
+            m = self._meta_host.to(self._dev, non_blocking=True)
+            self._meta_dev = m
+            n = m.shape[0]
+            dict.__setitem__(self, 'box_center', m[:, 0:2])
+            dict.__setitem__(self, 'box_size', m[:, 2])
+            dict.__setitem__(self, 'img_size', m[:, 3:5])
+            dict.__setitem__(self, 'do_flip', m[:, 5])
+            dict.__setitem__(self, 'inv_trans', m[:, 6:12].reshape(n, 2, 3))    # the reference returns the forward
+            dict.__setitem__(self, 'trans', m[:, 6:12].reshape(n, 2, 3).clone())  # transform twice
+        return self._meta_dev
+
+
 class hamer_inference:
     """Same constructor contract as the reference: ``cfg`` carries ``ckpt_path`` (and optionally
     ``mano_path``); alternatively pass an already built ``model``."""
@@ -60,7 +88,7 @@ class hamer_inference:
         self.std = 255. * np.array(self.cfg.MODEL.IMAGE_STD)
 
     # -- crop / warp / normalise -----------------------------------------------------------------
-    def prepare_batch_bbox(self, img_0, bboxs):
+    def prepare_batch_bbox(self, img_0, bboxs, _defer_upload=False):
         """infer.py:154-259.  Returns the same dict; 'img' is already on the device (the
         reference moves it there in estimate_from_rgb, infer.py:366-368)."""
         boxes, right = [], []
@@ -82,53 +110,55 @@ class hamer_inference:
             imgs.append(i); centers.append(c); sizes.append(s); trans.append(t)
         dev = self.device
         H, W = img_0.shape[:2]
-        trans = torch.from_numpy(np.concatenate(trans)).to(dev)
-        return {
-            'img': torch.cat(imgs) if len(imgs) > 1 else imgs[0],
-            'box_center': torch.from_numpy(np.concatenate(centers)).to(dev),
-            'box_size': torch.from_numpy(np.concatenate(sizes)).to(dev),
-            'img_size': torch.tensor([[W, H]] * n, dtype=torch.float32, device=dev),
-            'inv_trans': trans,            # the reference returns the forward transform twice
-            'trans': trans.clone(),
-            'do_flip': torch.tensor([0.0 if r else 1.0 for r in right], dtype=torch.float32, device=dev),
-        }
+        # every per-hand scalar goes to the device in ONE pinned upload; the dict entries are views of it
+        # (layout = the `meta` argument of hm_camera_postprocess, include/hamer_b200.h; columns 12..15 are the
+        # intrinsics estimate_from_rgb fills in)
+        meta = torch.zeros(n, META_COLS, dtype=torch.float32, pin_memory=True)
+        mv = meta.numpy()
+        mv[:, 0:2] = np.concatenate(centers)
+        mv[:, 2] = np.concatenate(sizes)
+        mv[:, 3] = W
+        mv[:, 4] = H
+        mv[:, 5] = [0.0 if r else 1.0 for r in right]
+        mv[:, 6:12] = np.concatenate(trans).reshape(n, 6)
+        batch = _Batch(img=torch.cat(imgs) if len(imgs) > 1 else imgs[0])
+        batch._meta_host, batch._dev = meta, dev
+        if not _defer_upload:
+            batch.meta_dev()
+        return batch
 
     # -- full per-image estimate -----------------------------------------------------------------
     @torch.no_grad()
     def estimate_from_rgb(self, img_0, detections, k_real=None):
         if not isinstance(detections, list) or len(detections) == 0:
             raise ValueError('Invalid detections format')                     # infer.py:360-361
-        batch = self.prepare_batch_bbox(img_0, detections)
-        out, params = self.model(batch)
-        pred_cam = out['pred_cam']
-        box_center, box_size = batch['box_center'], batch['box_size']
-        img_size, do_flip = batch['img_size'], batch['do_flip']
-        kp3d = out['pred_keypoints_3d']
-        kp3d[:, :, 0] = kp3d[:, :, 0] * do_flip.unsqueeze(1)                  # infer.py:392 (in place)
-        cam = pred_cam.clone()
-        cam[:, 1] = cam[:, 1] * (1.0 - 2.0 * do_flip.view(-1))               # infer.py:402-409
+        batch = self.prepare_batch_bbox(img_0, detections, _defer_upload=True)
+        mv = batch._meta_host.numpy()
+        W, H = float(mv[0, 3]), float(mv[0, 4])
         if k_real is not None:
-            k = torch.as_tensor(np.asarray(k_real) if not torch.is_tensor(k_real) else k_real,
-                                dtype=torch.float32, device=self.device)
-            if k.dim() == 2:
-                fx, fy, cx, cy = k[0, 0], k[1, 1], k[0, 2], k[1, 2]
+            k = (k_real.detach().cpu().numpy() if torch.is_tensor(k_real) else np.asarray(k_real)).astype(np.float32)
+            if k.ndim == 2:
+                mv[:, 12], mv[:, 13], mv[:, 14], mv[:, 15] = k[0, 0], k[1, 1], k[0, 2], k[1, 2]
             else:
-                fx, fy, cx, cy = k[:, 0, 0], k[:, 1, 1], k[:, 0, 2], k[:, 1, 2]
-            cam_t_full = custom_cam_crop_to_full(cam, box_center, box_size, img_size, fx, fy, cx, cy)
-            scaled_focal_length = fx.unsqueeze(0) if fx.dim() == 0 else fx
-            kp_cam = kp3d + cam_t_full.unsqueeze(1)
-            depth = kp_cam[:, :, 2:3] + 1e-9
-            u = kp_cam[:, :, 0:1] / depth * fx.reshape(-1, 1, 1) + cx.reshape(-1, 1, 1)
-            v = kp_cam[:, :, 1:2] / depth * fy.reshape(-1, 1, 1) + cy.reshape(-1, 1, 1)
-            kp2d = torch.cat([u, v], dim=-1)
+                mv[:, 12], mv[:, 13], mv[:, 14], mv[:, 15] = k[:, 0, 0], k[:, 1, 1], k[:, 0, 2], k[:, 1, 2]
+            per_hand_k = k.ndim != 2
         else:
-            scaled_focal_length = (self.cfg.EXTRA.FOCAL_LENGTH / self.cfg.MODEL.IMAGE_SIZE *
-                                   img_size.max(dim=1)[0])
-            cam_t_full = custom_cam_crop_to_full(cam, box_center, box_size, img_size,
-                                                 scaled_focal_length, scaled_focal_length,
-                                                 img_size[:, 0] / 2.0, img_size[:, 1] / 2.0)
-            kp2d = perspective_projection(kp3d, cam_t_full,
-                                          torch.stack([scaled_focal_length, scaled_focal_length], dim=1))
+            # scaled_focal_length = FOCAL_LENGTH / IMAGE_SIZE * max(img_size)  (infer.py:489-493), fp32 like torch
+            f = np.float32(self.cfg.EXTRA.FOCAL_LENGTH / self.cfg.MODEL.IMAGE_SIZE) * np.float32(max(W, H))
+            mv[:, 12] = f
+            mv[:, 13] = f
+            mv[:, 14] = np.float32(W) / np.float32(2.0)
+            mv[:, 15] = np.float32(H) / np.float32(2.0)
+            per_hand_k = True
+        fxfy_differ = not np.allclose(mv[:, 12], mv[:, 13])              # renderer.py:63 torch.allclose(fx, fy)
+        meta = batch.meta_dev()                                           # the one small host -> device copy of the frame
+        out, params = self.model(batch)
+        # kp3d x-flip (infer.py:392, in place), cam y-flip (:402-409), cam_crop_to_full (renderer.py:24-74) and the
+        # full-image projection (:474-486 / geometry.py:72-109) in one kernel, bit-identical to the torch expressions
+        cam_t_full, kp2d = self.model.engine.camera_postprocess(out['pred_cam'], out['pred_keypoints_3d'], meta,
+                                                                fxfy_differ, k_real is not None)
+        do_flip = batch['do_flip']
+        scaled_focal_length = meta[:, 12] if per_hand_k else meta[:1, 12]
         out['pred_keypoints_2d_full'] = kp2d
         out['pred_cam_t_full'] = cam_t_full
         out['img'] = batch['img']

@@ -119,6 +119,18 @@ int hm_mano_head(hm_ctx* ctx, const float* feats, int B, const hm_outputs* out, 
 int hm_mano_lbs(hm_ctx* ctx, const float* betas, const float* rotmats, const float* cam_t, int B,
                 float* verts, float* joints21, float* kp2d, void* stream);
 
+/* hm_camera_postprocess replaces the camera post-processing of hamer_inference.estimate_from_rgb
+ * (hamer/infer.py:382-528: kp3d x-flip :392, cam y-flip :402-409, cam_crop_to_full = hamer/hamer/utils/renderer.py:24-74,
+ * projection of the 21 joints into the full image :474-486 / utils/geometry.py:72-109).  All pointers are DEVICE:
+ *   pred_cam [n,3]; kp3d [n,21,3] (x is multiplied by do_flip in place, as the reference does);
+ *   meta [n, meta_stride] float32 per hand: 0,1 box_center  2 box_size  5 do_flip (1 = left hand)  12 fx  13 fy  14 cx  15 cy
+ *   (other columns free for the caller: the Python mirror keeps img_size and the crop transform there);
+ *   fxfy_differ: the reference's batch-level `not torch.allclose(fx, fy)`; add_center: 1 = intrinsics given
+ *   (u = X/(Z+1e-9)*fx + cx), 0 = default focal (u = X/Z*f, zero camera centre);
+ *   outputs cam_t_full [n,3], kp2d_full [n,21,2].  fp32 results are bit-identical to the reference's PyTorch expressions. */
+int hm_camera_postprocess(hm_ctx* ctx, const float* pred_cam, float* kp3d, const float* meta, int meta_stride,
+                          int fxfy_differ, int add_center, int n, float* cam_t_full, float* kp2d_full, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels hm_forward(B) launches (for bench.py's gpu_launches). */
 int hm_forward_launch_count(const hm_ctx* ctx);

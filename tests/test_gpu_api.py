@@ -114,3 +114,45 @@ def test_deterministic_mode_is_batch_invariant(seeded_images, oracle_model):
     c, _ = m({'img': seeded_images.cuda()})
     assert torch.equal(a['pred_vertices'], c['pred_vertices'])
     assert torch.equal(b['pred_vertices'][:2], a['pred_vertices']) and torch.equal(b['pred_vertices'][4:], a['pred_vertices'])
+
+
+@pytest.mark.parametrize('use_k', [False, True])
+def test_camera_postprocess_kernel_matches_torch_bitwise(model, use_k):
+    """hm_camera_postprocess against the reference's PyTorch expressions (renderer.py:24-74, infer.py:392-486):
+    separately rounded fp32 operations in the same order -> identical bits."""
+    from hamer_yolo_b200.inference import custom_cam_crop_to_full, perspective_projection, META_COLS
+    g = torch.Generator().manual_seed(11)
+    n = 37
+    cam = torch.stack([0.6 + torch.rand(n, generator=g), torch.randn(n, generator=g) * 0.2, torch.randn(n, generator=g) * 0.2], 1)
+    kp3d = torch.randn(n, 21, 3, generator=g) * 0.08
+    meta = torch.zeros(n, META_COLS)
+    meta[:, 0] = torch.rand(n, generator=g) * 1920
+    meta[:, 1] = torch.rand(n, generator=g) * 1080
+    meta[:, 2] = 80 + torch.rand(n, generator=g) * 400
+    meta[:, 3], meta[:, 4] = 1920, 1080
+    meta[:, 5] = (torch.rand(n, generator=g) < 0.5).float()
+    if use_k:
+        meta[:, 12], meta[:, 13], meta[:, 14], meta[:, 15] = 1400.0, 1390.0, 955.0, 541.0
+    else:
+        meta[:, 12] = meta[:, 13] = 5000.0 / 256 * 1920
+        meta[:, 14], meta[:, 15] = 960.0, 540.0
+    dev = model.device
+    cam_d, kp_d, meta_d = cam.to(dev), kp3d.to(dev), meta.to(dev)
+    # reference expressions on the same device
+    flip = meta_d[:, 5]
+    kp_ref = kp_d.clone()
+    kp_ref[:, :, 0] = kp_ref[:, :, 0] * flip.unsqueeze(1)
+    c = cam_d.clone()
+    c[:, 1] = c[:, 1] * (1.0 - 2.0 * flip)
+    t_ref = custom_cam_crop_to_full(c, meta_d[:, 0:2], meta_d[:, 2], meta_d[:, 3:5], meta_d[:, 12], meta_d[:, 13],
+                                    meta_d[:, 14], meta_d[:, 15])
+    if use_k:
+        p = kp_ref + t_ref.unsqueeze(1)
+        depth = p[:, :, 2:3] + 1e-9
+        uv_ref = torch.cat([p[:, :, 0:1] / depth * meta_d[:, 12].reshape(-1, 1, 1) + meta_d[:, 14].reshape(-1, 1, 1),
+                            p[:, :, 1:2] / depth * meta_d[:, 13].reshape(-1, 1, 1) + meta_d[:, 15].reshape(-1, 1, 1)], dim=-1)
+    else:
+        uv_ref = perspective_projection(kp_ref, t_ref, torch.stack([meta_d[:, 12], meta_d[:, 13]], dim=1))
+    differ = not torch.allclose(meta_d[:, 12], meta_d[:, 13])
+    t, uv = model.engine.camera_postprocess(cam_d, kp_d, meta_d, differ, use_k)
+    assert torch.equal(t, t_ref) and torch.equal(uv, uv_ref) and torch.equal(kp_d, kp_ref)
