@@ -205,6 +205,31 @@ def test_mano_lbs_three_kernel_path_agrees(engine, oracle_model):
     assert (k - k2).abs().max().item() * 256 < 1e-2            # px
 
 
+@pytest.mark.parametrize('B', [1, 37, 129, 300])
+def test_mano_lbs_writes_stay_inside_the_outputs(engine, B):
+    """Guard bands around every output of hm_mano_lbs (ragged hand tiles, the partial last vertex group, fingertip and
+    projection writes): nothing outside [B,778,3] / [B,21,3] / [B,21,2] may change, everything inside must."""
+    import ctypes as C
+    betas, rot, cam_t = random_mano_inputs(B, 50 + B)
+    dev = engine.device
+    pad = 4096
+    bufs = {}
+    for name, numel in (('verts', B * 778 * 3), ('joints', B * 63), ('kp2d', B * 42)):
+        bufs[name] = torch.full((pad + numel + pad,), float('nan'), device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    b_d, r_d, c_d = betas.to(dev), rot.to(dev), cam_t.to(dev)
+    with torch.cuda.device(dev):
+        engine.check(engine.lib.hm_mano_lbs(engine.h, ptr(b_d), ptr(r_d), ptr(c_d), B, ptr(bufs['verts'][pad:]),
+                                            ptr(bufs['joints'][pad:]), ptr(bufs['kp2d'][pad:]), engine.stream()))
+    torch.cuda.synchronize()
+    for name, t in bufs.items():
+        assert torch.isnan(t[:pad]).all() and torch.isnan(t[-pad:]).all(), name
+        assert torch.isfinite(t[pad:-pad]).all(), name
+    v_ref, j_ref, k_ref = engine.mano_lbs(b_d, r_d, c_d)
+    assert torch.equal(bufs['verts'][pad:-pad].view(B, 778, 3), v_ref)
+    assert torch.equal(bufs['joints'][pad:-pad].view(B, 21, 3), j_ref) and torch.equal(bufs['kp2d'][pad:-pad].view(B, 21, 2), k_ref)
+
+
 def test_mano_lbs_full_size_properties(engine):
     """BASELINE config 4 size (65536 hands): batch-position independence (bit-exact) and
     global-rotation equivariance about the root joint."""
