@@ -87,10 +87,12 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int mblk = 0; mblk < 2; ++mblk) {
+    // gridDim.z == 2 (few crops: 32 B CTAs would leave most SMs idle): one query block per CTA instead of both
+    const int mblk0 = gridDim.z == 2 ? (int)blockIdx.z : 0, mblk1 = gridDim.z == 2 ? mblk0 + 1 : 2;
+    for (int mblk = mblk0; mblk < mblk1; ++mblk) {
         const int q0 = mblk * 128;
         const int q_rows = (mblk == 0) ? 128 : (AT5_T - 128);            // valid query rows of this block
-        const uint32_t par = (uint32_t)mblk;                             // mbarrier phase parity of this pass
+        const uint32_t par = (uint32_t)(mblk - mblk0);                   // mbarrier phase parity of this pass
         // ---- 2. S = Q K^T (block 1's descriptors start 128 rows further down; its rows 64..127 are
         //         don't-care data read from the neighbouring tile) ---------------------------------------
         if (tid == 0) {

@@ -344,8 +344,8 @@ int backbone_impl(hm_ctx* c, const float* img, int B, float* feats_out, cudaStre
           if ((rc = run_gemm(c, EPI_BIAS_BF16, c->tm_xn, w.tm_qkv, M, 3 * DM, DM, w.b_qkv, c->qkv, nullptr, s))) return rc; }
         { ProfScope ps(c, s, PC_ATTENTION);
           if (c->att_legacy) launch_pdl(vit_attention_kernel, dim3(16, B), dim3(ATT_THREADS), ATT_SMEM_BYTES, s, c->qkv, c->att, att_scale);
-          else launch_pdl(vit_attention_tc5_kernel<false>, dim3(16, B), dim3(AT5_THREADS), AT5_SMEM_BYTES, s,
-                          c->tm_att128, c->tm_att32, c->att, att_scale, nullptr); }
+          else launch_pdl(vit_attention_tc5_kernel<false>, dim3(16, B, (32 * B <= 2 * c->num_sms) ? 2 : 1), dim3(AT5_THREADS),
+                          AT5_SMEM_BYTES, s, c->tm_att128, c->tm_att32, c->att, att_scale, nullptr); }
         { ProfScope ps(c, s, PC_GEMM_PROJ);
           if ((rc = run_gemm(c, EPI_BIAS_RESID_F32, c->tm_att, w.tm_proj, M, DM, DM, w.b_proj, c->x, nullptr, s))) return rc; }
         { ProfScope ps(c, s, PC_LAYERNORM); launch_ln<10, __half>(c->x, w.ln2_g, w.ln2_b, c->xn, M, 1e-6f, s); }
