@@ -86,9 +86,9 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
 
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
     // gridDim.z == 2 (few crops: 32 B CTAs would leave most SMs idle): one query block per CTA instead of both
     const int mblk0 = gridDim.z == 2 ? (int)blockIdx.z : 0, mblk1 = gridDim.z == 2 ? mblk0 + 1 : 2;
+#pragma unroll 1
     for (int mblk = mblk0; mblk < mblk1; ++mblk) {
         const int q0 = mblk * 128;
         const int q_rows = (mblk == 0) ? 128 : (AT5_T - 128);            // valid query rows of this block
