@@ -117,6 +117,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // Two elements per instruction with the packed fp32 pipe of sm_100 (FFMA2 / FMUL2): the fc1 epilogue
 // is issue-bound, so halving the FMA/MUL count of the polynomial is what matters (MUFU stays scalar).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    // z = |x| / sqrt 2;  q = 1 - erf(z) = poly(t) t exp(-z^2), t = 1 / (1 + p z);  gelu(x) = max(x, 0) - (z / sqrt 2) q
+    // (x >= 0: x - x q / 2;  x < 0: x q / 2 = -|x| q / 2): no select, one packed FMA for the final combination
     const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
     const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
     float2 t, e;
@@ -130,8 +132,8 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
     const float2 q = __fmul2_rn(__fmul2_rn(poly, t), e);
-    const float2 hxq = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), q);
-    return make_float2(x.x >= 0.f ? x.x - hxq.x : hxq.x, x.y >= 0.f ? x.y - hxq.y : hxq.y);
+    const float2 nz = __fmul2_rn(z, make_float2(-0.70710678118654752440f, -0.70710678118654752440f));   // -|x| / 2
+    return __ffma2_rn(nz, q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
