@@ -311,27 +311,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         __half* out = reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float v[8];
+                            float2 v[4];                        // packed adds: the accumulator registers are adjacent pairs
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
                                 const float4 b = __ldg(bias4 + j * 2 + q);
-                                v[q * 4 + 0] = __uint_as_float(r[j * 8 + q * 4 + 0]) + b.x;
-                                v[q * 4 + 1] = __uint_as_float(r[j * 8 + q * 4 + 1]) + b.y;
-                                v[q * 4 + 2] = __uint_as_float(r[j * 8 + q * 4 + 2]) + b.z;
-                                v[q * 4 + 3] = __uint_as_float(r[j * 8 + q * 4 + 3]) + b.w;
+                                v[q * 2 + 0] = __fadd2_rn(make_float2(__uint_as_float(r[j * 8 + q * 4 + 0]), __uint_as_float(r[j * 8 + q * 4 + 1])),
+                                                          make_float2(b.x, b.y));
+                                v[q * 2 + 1] = __fadd2_rn(make_float2(__uint_as_float(r[j * 8 + q * 4 + 2]), __uint_as_float(r[j * 8 + q * 4 + 3])),
+                                                          make_float2(b.z, b.w));
                             }
                             if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-                                for (int e = 0; e < 8; e += 2) {
-                                    const float2 g = gelu_erf2(make_float2(v[e], v[e + 1]));
-                                    v[e] = g.x; v[e + 1] = g.y;
-                                }
+                                for (int e = 0; e < 4; ++e) v[e] = gelu_erf2(v[e]);
                             }
                             uint4 o;
-                            o.x = pack_act2(v[0], v[1]);
-                            o.y = pack_act2(v[2], v[3]);
-                            o.z = pack_act2(v[4], v[5]);
-                            o.w = pack_act2(v[6], v[7]);
+                            o.x = pack_act2(v[0].x, v[0].y);
+                            o.y = pack_act2(v[1].x, v[1].y);
+                            o.z = pack_act2(v[2].x, v[2].y);
+                            o.w = pack_act2(v[3].x, v[3].y);
                             *reinterpret_cast<uint4*>(out + j * 8) = o;
                         }
                     }
@@ -346,9 +343,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 b = with_bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        float4 v;
-                        v.x = __uint_as_float(r[j * 4 + 0]) + b.x; v.y = __uint_as_float(r[j * 4 + 1]) + b.y;
-                        v.z = __uint_as_float(r[j * 4 + 2]) + b.z; v.w = __uint_as_float(r[j * 4 + 3]) + b.w;
+                        const float2 lo = __fadd2_rn(make_float2(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1])), make_float2(b.x, b.y));
+                        const float2 hi = __fadd2_rn(make_float2(__uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3])), make_float2(b.z, b.w));
+                        const float4 v = make_float4(lo.x, lo.y, hi.x, hi.y);
                         *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
                     }
                     ptx::fence_proxy_async();            // generic-proxy writes -> visible to TMA
