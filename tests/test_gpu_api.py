@@ -156,3 +156,33 @@ def test_camera_postprocess_kernel_matches_torch_bitwise(model, use_k):
     differ = not torch.allclose(meta_d[:, 12], meta_d[:, 13])
     t, uv = model.engine.camera_postprocess(cam_d, kp_d, meta_d, differ, use_k)
     assert torch.equal(t, t_ref) and torch.equal(uv, uv_ref) and torch.equal(kp_d, kp_ref)
+
+
+def test_opt_in_programmatic_dependent_launch(tmp_path):
+    """HM_PDL=1 (launches carry the programmatic-stream-serialization attribute; every kernel waits on
+    griddepcontrol.wait): same results as the default launches, eager and graph-replayed."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'pdl_run.py'
+    script.write_text(
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from hamer_yolo_b200 import load_hamer, synthetic_mano\n"
+        "from hamer_yolo_b200.weights import random_state_dict\n"
+        "dev = torch.device('cuda:0')\n"
+        "m, _ = load_hamer(state_dict=random_state_dict(seed=3, device=dev), mano=synthetic_mano(0), device='cuda:0',\n"
+        "                  max_batch=4, deterministic=True)\n"
+        "img = torch.randn(3, 3, 256, 256, generator=torch.Generator().manual_seed(5)).to(dev)\n"
+        "a, _ = m({'img': img})\n"
+        "b, _ = m({'img': img})\n"                      # second call replays the captured graph
+        "assert torch.equal(a['pred_vertices'], b['pred_vertices'])\n"
+        "torch.save(a['pred_vertices'].cpu(), sys.argv[1])\n")
+    outs = []
+    for pdl in ('0', '1'):
+        out = tmp_path / f'verts_{pdl}.pt'
+        env = dict(os.environ, HM_PDL=pdl)
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env=env, timeout=240)
+        outs.append(torch.load(out))
+    assert torch.equal(outs[0], outs[1])
