@@ -4,6 +4,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <array>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -126,6 +127,8 @@ struct hm_ctx {
 
     // preprocess
     uint8_t* frame_dev = nullptr;
+    std::vector<std::array<double, 4>> crop_win;   // per crop: source window x0, x1, y0, y1 (host frames: what gets uploaded)
+    std::vector<std::array<long, 4>> crop_rect;
     CropParams* crop_host = nullptr;   // pinned
     CropParams* crop_dev = nullptr;
     float* lut = nullptr;              // [3][256]
@@ -561,6 +564,8 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     CA(dev_alloc(c, &c->lut, (size_t)768));
     if (cfg->max_frame_bytes > 0) CA(dev_alloc(c, &c->frame_dev, (size_t)cfg->max_frame_bytes));
     CA(cudaMallocHost(reinterpret_cast<void**>(&c->crop_host), Bm * sizeof(CropParams)));
+    c->crop_win.resize(Bm);
+    c->crop_rect.resize(Bm);
     CA(cudaEventCreateWithFlags(&c->crop_event, cudaEventDisableTiming));
     // the workspace is read by TMA beyond the live rows of a partial tile: keep it finite
     CA(cudaMemset(c->patches, 0, Mmax * KPATCH * 2));
@@ -989,6 +994,8 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
         box_to_affine(box, &cx, &cy, &size, M);
         if (cy - 0.5 * size < band_lo) band_lo = cy - 0.5 * size;
         if (cy + 0.5 * size > band_hi) band_hi = cy + 0.5 * size;
+        c->crop_win[i][0] = cx - 0.5 * size; c->crop_win[i][1] = cx + 0.5 * size;
+        c->crop_win[i][2] = cy - 0.5 * size; c->crop_win[i][3] = cy + 0.5 * size;
         invert_affine(M, c->crop_host[i].m);
         c->crop_host[i].flip = is_right[i] ? 0 : 1;
         c->crop_host[i].pad = 0;
@@ -1006,9 +1013,28 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
         long r0 = (long)floor(band_lo) - 4, r1 = (long)ceil(band_hi) + 4;
         if (r0 < 0) r0 = 0;
         if (r1 > H - 1) r1 = H - 1;
-        if (r1 >= r0)
+        // per-crop rectangles when together they are much smaller than the band (hands scattered over the frame)
+        size_t rect_bytes = 0;
+        for (int i = 0; i < n; ++i) {
+            long x0 = (long)floor(c->crop_win[i][0]) - 4, x1 = (long)ceil(c->crop_win[i][1]) + 4;
+            long y0 = (long)floor(c->crop_win[i][2]) - 4, y1 = (long)ceil(c->crop_win[i][3]) + 4;
+            if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0; if (x1 > W - 1) x1 = W - 1; if (y1 > H - 1) y1 = H - 1;
+            c->crop_rect[i][0] = x0; c->crop_rect[i][1] = x1; c->crop_rect[i][2] = y0; c->crop_rect[i][3] = y1;
+            if (x1 >= x0 && y1 >= y0) rect_bytes += (size_t)(x1 - x0 + 1) * 3 * (size_t)(y1 - y0 + 1);
+        }
+        const size_t band_bytes = r1 >= r0 ? (size_t)(r1 - r0 + 1) * row_stride : 0;
+        if (rect_bytes + (size_t)n * 65536 < band_bytes) {       // 64 KB per copy ~ the fixed cost of a pageable 2-D copy
+            for (int i = 0; i < n; ++i) {
+                const long x0 = c->crop_rect[i][0], x1 = c->crop_rect[i][1], y0 = c->crop_rect[i][2], y1 = c->crop_rect[i][3];
+                if (x1 < x0 || y1 < y0) continue;               // window entirely outside the frame: constant border only
+                const size_t off = (size_t)y0 * row_stride + (size_t)x0 * 3;
+                HM_CUDA(c, cudaMemcpy2DAsync(c->frame_dev + off, (size_t)row_stride, frame_bgr + off, (size_t)row_stride,
+                                             (size_t)(x1 - x0 + 1) * 3, (size_t)(y1 - y0 + 1), cudaMemcpyHostToDevice, s));
+            }
+        } else if (r1 >= r0) {
             HM_CUDA(c, cudaMemcpyAsync(c->frame_dev + (size_t)r0 * row_stride, frame_bgr + (size_t)r0 * row_stride,
-                                       (size_t)(r1 - r0 + 1) * row_stride, cudaMemcpyHostToDevice, s));
+                                       band_bytes, cudaMemcpyHostToDevice, s));
+        }
         frame = c->frame_dev;
     }
     HM_CUDA(c, cudaMemcpyAsync(c->crop_dev, c->crop_host, (size_t)n * sizeof(CropParams), cudaMemcpyHostToDevice, s));
