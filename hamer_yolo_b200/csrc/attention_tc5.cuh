@@ -51,9 +51,9 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t sQ = sbase, sK = sbase + AT5_TA, sV = sbase + 2 * AT5_TA;
     const uint32_t sQb = sbase + 3 * AT5_TA, sKb = sQb + AT5_TB, sVb = sKb + AT5_TB;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AT5_DATA);        // [0] S done, [1] O done, [2] loads
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
-    float* xch = reinterpret_cast<float*>(bar + 4);                      // [2][128] row max / row sum exchange
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AT5_DATA);        // [0] S done, [1] O done, [2] Q, K landed, [3] V landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 4);
+    float* xch = reinterpret_cast<float*>(bar + 5);                      // [2][128] row max / row sum exchange
 
     const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -64,15 +64,19 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
         ptx::mbar_init(&bar[0], 1);
         ptx::mbar_init(&bar[1], 1);
         ptx::mbar_init(&bar[2], 1);
+        ptx::mbar_init(&bar[3], 1);
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&tm128);
         ptx::prefetch_tmap(&tm32);
         ptx::griddep_wait();            // qkv comes from the previous kernel; everything below depends on these loads
-        ptx::mbar_arrive_expect_tx(&bar[2], AT5_DATA);
+        // V is first needed by the PV MMAs of the first pass: its own barrier lets S = Q K^T and the softmax start
+        // as soon as Q and K are there
+        ptx::mbar_arrive_expect_tx(&bar[2], 2 * (AT5_TA + AT5_TB));
+        ptx::mbar_arrive_expect_tx(&bar[3], AT5_TA + AT5_TB);
         const int row0 = b * AT5_T, col = h * AT5_D;
         for (int m = 0; m < 3; ++m) {                                    // Q, K, V column blocks of qkv
-            ptx::tma_load_2d(smem + m * AT5_TA, &tm128, &bar[2], m * 1280 + col, row0);
-            ptx::tma_load_2d(smem + 3 * AT5_TA + m * AT5_TB, &tm32, &bar[2], m * 1280 + col + 64, row0);
+            ptx::tma_load_2d(smem + m * AT5_TA, &tm128, &bar[m == 2 ? 3 : 2], m * 1280 + col, row0);
+            ptx::tma_load_2d(smem + 3 * AT5_TA + m * AT5_TB, &tm32, &bar[m == 2 ? 3 : 2], m * 1280 + col + 64, row0);
         }
     }
     if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, AT5_TMEM_COLS);
@@ -171,6 +175,7 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
 
         // ---- 4. O = P V (A from TMEM; V MN-major: 8-token groups 1024 B / 256 B apart) ---------------------
         if (tid == 0) {
+            ptx::mbar_wait(&bar[3], 0);                                   // V (completed once; later waits return at once)
             ptx::tc_fence_after();
             constexpr uint32_t idesc64 = ptx::make_idesc_f16kind_f32(0, 0, 128, 64, 0, 1);
             constexpr uint32_t idesc16 = ptx::make_idesc_f16kind_f32(0, 0, 128, 16, 0, 1);
