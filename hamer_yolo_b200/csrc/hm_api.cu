@@ -966,6 +966,12 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
             return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed (fused)");
     }
     for (int j = 0; j < 16; ++j) c->mano.parents[j] = parents[j];
+    c->mano.max_depth = 0;
+    for (int j = 0; j < 16; ++j) {
+        int d = 0;
+        for (int q = parents[j]; q >= 0; q = parents[q]) ++d;
+        if (d > c->mano.max_depth) c->mano.max_depth = d;
+    }
     for (int q = 0; q < 5; ++q) c->mano.tip_ids[q] = tip_ids[q];
     for (int q = 0; q < 21; ++q) c->mano.joint_map[q] = joint_map[q];
     c->mano_set = true;

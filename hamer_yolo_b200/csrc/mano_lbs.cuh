@@ -54,6 +54,7 @@ struct ManoDevice {
     int32_t parents[16];
     int32_t tip_ids[5];
     int32_t joint_map[21];
+    int32_t max_depth;         // depth of the kinematic tree (longest ancestor chain)
     int32_t chain_slot[16];    // output slot (0..20) of chain joint j, -1 = not in joint_map
     int32_t tip_slot[5];       // output slot of fingertip q
 };
@@ -99,9 +100,10 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
                 if (kk < 10) c = be[kk];
                 else if (FUSED && kk >= 145 && kk < 155) c = be[kk - 145];   // betas again, for the "shape lo" basis columns
                 else if (kk < 145) {
-                    const int e = kk - 10;                  // (joint-1)*9 + row*3 + col
-                    const int e9 = e % 9;
-                    c = R[9 + e] - ((e9 == 0 || e9 == 4 || e9 == 8) ? 1.f : 0.f);
+                    // kk - 10 = (joint-1)*9 + row*3 + col; the diagonal entries ((kk - 10) % 9 in {0,4,8}) come from a
+                    // 160-bit constant mask instead of an integer modulo per element
+                    constexpr uint32_t DIAG[5] = {0x188c4400u, 0x88c46231u, 0x8c462311u, 0xc4623118u, 0x00011188u};
+                    c = R[kk - 1] - (float)((DIAG[kk >> 5] >> (kk & 31)) & 1u);
                 }
                 v[q] = c;
             }
@@ -134,7 +136,7 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
     }
 #pragma unroll
     for (int e = 0; e < 12; ++e) G[e] = L[e];
-    for (int lev = 0; lev < MANO_J; ++lev) {              // uniform trip count; exits early below
+    for (int lev = 0; lev <= m.max_depth; ++lev) {        // host-computed tree depth (3 for MANO): one barrier per level
         if (depth == lev) {
             if (pa >= 0) {
                 const float* P = sG[slot][pa];
@@ -151,7 +153,6 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
             for (int e = 0; e < 12; ++e) sG[slot][j][e] = G[e];
         }
         __syncthreads();
-        if (lev >= 3 && __syncthreads_and(depth <= lev)) break;   // MANO's tree has depth 3
     }
     if (!live) return;
     // ---- outputs: A = G with translation t - R_glob J_rest; posed joint = translation of G --------
