@@ -14,7 +14,7 @@ c_float_p = C.POINTER(C.c_float)
 class HmConfig(C.Structure):
     _fields_ = [('max_batch', C.c_int32), ('max_frame_bytes', C.c_int32),
                 ('gemm_cta_group', C.c_int32), ('attention_legacy', C.c_int32), ('mano_legacy', C.c_int32),
-                ('deterministic', C.c_int32), ('reserved', C.c_int32 * 2)]
+                ('deterministic', C.c_int32), ('split_weights', C.c_int32), ('reserved', C.c_int32 * 1)]
 
 
 class HmOutputs(C.Structure):

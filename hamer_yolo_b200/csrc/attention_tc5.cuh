@@ -206,8 +206,7 @@ vit_attention_tc5_kernel(const __grid_constant__ CUtensorMap tm128, const __grid
                     uint32_t w[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const __half2 hv = __floats2half2_rn(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
-                        w[j] = *reinterpret_cast<const uint32_t*>(&hv);
+                        w[j] = ptx::pack_half2_sat(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
                     }
                     *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);

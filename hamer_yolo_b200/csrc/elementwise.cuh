@@ -62,10 +62,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         o.z = v[i].z * rstd * g.z + b.z;
         o.w = v[i].w * rstd * g.w + b.w;
         if constexpr (sizeof(OutT) == 2) {
-            __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
             uint2 p;
-            p.x = *reinterpret_cast<uint32_t*>(&lo);
-            p.y = *reinterpret_cast<uint32_t*>(&hi);
+            p.x = ptx::pack_half2_sat(o.x, o.y);
+            p.y = ptx::pack_half2_sat(o.z, o.w);
             reinterpret_cast<uint2*>(y + (size_t)row * D)[i * 32 + lane] = p;
         } else {
             reinterpret_cast<float4*>(y + (size_t)row * D)[i * 32 + lane] = o;

@@ -111,12 +111,15 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, c
                                  int num_sms, cudaStream_t stream) {
     using Cfg = GemmCfg<CTA_GROUP, BN, EPI>;
     auto kern = gemm_bf16_tn_kernel<CTA_GROUP, BN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: one flag per ordinal (several contexts on different GPUs in one process)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int tile_m = GEMM_BM * CTA_GROUP;
     const int tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BN);

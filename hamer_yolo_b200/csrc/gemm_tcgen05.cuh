@@ -54,6 +54,9 @@ struct GemmParams {
     int ksplit_workers; // worker count the split was planned for (set by gemm_launch)
     int ksplit;         // EPI_BIAS_RESID_F32 only: the tiles of the last, partial wave are split into `ksplit`
                         // K-slices (each slice reduce-adds its partial product; slice 0 carries the bias); <= 1 = off
+    int a_kwrap;        // > 0: A has only a_kwrap k-blocks and is re-read for k-blocks >= a_kwrap, i.e. the product is
+                        // A * [W_hi | W_lo]^T with W stored as [N, 2K] (hm_config.split_weights: fp32-exact weights as
+                        // the sum of two fp16 matrices); 0 = plain GEMM
 };
 
 // Work items of the persistent loop: full tiles first, then the K-slices of the tail tiles.
@@ -136,10 +139,7 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     return __ffma2_rn(nz, q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
-__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) { return ptx::pack_half2_sat(lo, hi); }
 
 template <int CTA_GROUP, int BN, int EPI>
 __global__ void __launch_bounds__(GemmCfg<CTA_GROUP, BN, EPI>::THREADS, 1)
@@ -221,18 +221,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 const int m0 = m_blk * tile_m + (int)cta_rank * GEMM_BM;
                 const int n0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    const int ka = (p.a_kwrap > 0 && kb >= p.a_kwrap) ? kb - p.a_kwrap : kb;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if constexpr (CTA_GROUP == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage],
-                                         kb * GEMM_BK, m0);
+                                         ka * GEMM_BK, m0);
                         ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage],
                                          kb * GEMM_BK, n0);
                     } else {
                         if (is_leader)
                             ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                         ptx::tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &tmap_a,
-                                             &full_bar[stage], kb * GEMM_BK, m0);
+                                             &full_bar[stage], ka * GEMM_BK, m0);
                         ptx::tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES, &tmap_b,
                                              &full_bar[stage], kb * GEMM_BK, n0);
                     }

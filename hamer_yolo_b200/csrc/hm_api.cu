@@ -59,17 +59,26 @@ struct HeadLayerW {
     const float *w1, *b1, *w2, *b2;                   // feed-forward
 };
 
-// fp32 -> 16-bit weight operand (fmt 1 = bf16, 0 = fp16), round to nearest even
+// fp32 -> 16-bit weight operand (fmt 1 = bf16, 0 = fp16), round to nearest even; fp16 saturates at +-65,504
+// instead of overflowing to inf.
+// split != 0 (hm_config.split_weights, fp16 only): in is [rows, K], out is [rows, 2K] = [hi | lo] with hi = fp16(w),
+// lo = fp16(w - hi): hi + lo carries ~21 mantissa bits of w, the GEMM runs over K' = 2K re-reading A
+// (GemmParams::a_kwrap).
 __global__ void f32_to_w16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, size_t n,
-                                  int fmt) {
+                                  int fmt, int split, int K) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (fmt == 1) {
         const __nv_bfloat16 v = __float2bfloat16_rn(in[i]);
         out[i] = *reinterpret_cast<const uint16_t*>(&v);
+    } else if (!split) {
+        out[i] = ptx::half_bits_sat(in[i]);
     } else {
-        const __half v = __float2half_rn(in[i]);
-        out[i] = *reinterpret_cast<const uint16_t*>(&v);
+        const size_t r = i / (size_t)K, k = i - r * (size_t)K;
+        const uint16_t hi = ptx::half_bits_sat(in[i]);
+        const float hf = __half2float(*reinterpret_cast<const __half*>(&hi));
+        out[r * 2 * (size_t)K + k] = hi;
+        out[r * 2 * (size_t)K + K + k] = ptx::half_bits_sat(in[i] - hf);
     }
 }
 
@@ -82,6 +91,7 @@ struct hm_ctx {
     std::string err;
     GemmPlan plan{2, 256};
     bool deterministic = false;
+    bool split_w = false;        // hm_config.split_weights: backbone weights as fp16 hi + lo pairs, K doubled
     int small_m = 384;           // rows at or below which the backbone GEMMs use single-CTA 128 x 128 tiles (HM_SMALL_M)
 
     std::map<std::string, DevTensor> w;   // every state-dict entry, on the device
@@ -134,6 +144,8 @@ struct hm_ctx {
     float* lut = nullptr;              // [3][256]
     cudaEvent_t crop_event = nullptr;
     bool crop_event_pending = false;
+    cudaEvent_t crop_kernel_event = nullptr;   // the last crop kernel has finished reading crop_dev / frame_dev
+    bool crop_kernel_recorded = false;
 
     std::vector<void*> allocs;
 
@@ -322,6 +334,7 @@ int run_gemm(hm_ctx* c, int epi, const CUtensorMap& ta, const CUtensorMap& tb, i
              const float* bias, void* out, const float* pos, cudaStream_t s) {
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.pos = pos; p.pos_rows = TOK;
+    if (c->split_w) { p.K = 2 * K; p.a_kwrap = K / GEMM_BK; }   // W = [hi | lo]: second pass over A against the low halves
     p.b_format = c->b_format;
     p.ksplit = c->deterministic ? -1 : 0;   // -1: never split K (fixed fp32 summation order, batch-invariant results)
     // Few rows (video regime, a handful of hands per frame): 256 x 256 CTA-pair tiles leave most SMs idle and every
@@ -534,6 +547,7 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     c->att_legacy = cfg->attention_legacy != 0;
     c->mano_legacy = cfg->mano_legacy != 0;
     c->deterministic = cfg->deterministic != 0;
+    c->split_w = cfg->split_weights != 0;
     if (const char* e = getenv("HM_SMALL_M")) c->small_m = atoi(e);
     if (!get_tmap_encode()) return bail(HM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
@@ -567,6 +581,7 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     c->crop_win.resize(Bm);
     c->crop_rect.resize(Bm);
     CA(cudaEventCreateWithFlags(&c->crop_event, cudaEventDisableTiming));
+    CA(cudaEventCreateWithFlags(&c->crop_kernel_event, cudaEventDisableTiming));
     // the workspace is read by TMA beyond the live rows of a partial tile: keep it finite
     CA(cudaMemset(c->patches, 0, Mmax * KPATCH * 2));
     CA(cudaMemset(c->xn, 0, Mmax * DM * 2));
@@ -619,6 +634,7 @@ void hm_destroy(hm_ctx* c) {
     for (auto& kv : c->w) { cudaFree(kv.second.f32); cudaFree(kv.second.bf16); }
     if (c->crop_host) cudaFreeHost(c->crop_host);
     if (c->crop_event) cudaEventDestroy(c->crop_event);
+    if (c->crop_kernel_event) cudaEventDestroy(c->crop_kernel_event);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     delete c;
 }
@@ -632,19 +648,27 @@ int hm_set_weight(hm_ctx* c, const char* name, const float* data, const int64_t*
     const std::string key(name);
     auto old = c->w.find(key);
     if (old != c->w.end()) { cudaFree(old->second.f32); cudaFree(old->second.bf16); c->w.erase(old); }
+    c->finalized = false;
     HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.f32), t.numel * 4));
-    HM_CUDA(c, cudaMemcpy(t.f32, data, t.numel * 4, cudaMemcpyHostToDevice));
-    if (is_backbone_matrix(key)) {
-        // tensor-core operand: keep only the 16-bit (fp16) copy
-        HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.bf16), t.numel * 2));
-        f32_to_w16_kernel<<<(unsigned)((t.numel + 255) / 256), 256>>>(
-            t.f32, reinterpret_cast<uint16_t*>(t.bf16), t.numel, (int)c->b_format);
-        HM_CUDA(c, cudaDeviceSynchronize());
+    cudaError_t e = cudaMemcpy(t.f32, data, t.numel * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && is_backbone_matrix(key) && ndim == 2) {
+        // tensor-core operand: keep only the 16-bit (fp16) copy ([hi | lo] pairs with split_weights)
+        const int split = c->split_w ? 1 : 0;
+        e = cudaMalloc(reinterpret_cast<void**>(&t.bf16), t.numel * 2 * (split + 1));
+        if (e == cudaSuccess) {
+            f32_to_w16_kernel<<<(unsigned)((t.numel + 255) / 256), 256>>>(
+                t.f32, reinterpret_cast<uint16_t*>(t.bf16), t.numel, (int)c->b_format, split, (int)shape[1]);
+            e = cudaDeviceSynchronize();
+        }
         cudaFree(t.f32);
         t.f32 = nullptr;
     }
+    if (e != cudaSuccess) {
+        cudaFree(t.f32);
+        cudaFree(t.bf16);
+        return fail(c, HM_ERR_CUDA, std::string("hm_set_weight(") + name + "): " + cudaGetErrorString(e));
+    }
     c->w[key] = t;
-    c->finalized = false;
     return HM_OK;
 }
 
@@ -697,8 +721,9 @@ int hm_finalize_weights(hm_ctx* c) {
         return cudaMemcpy(h.data(), t->f32, t->numel * 4, cudaMemcpyDeviceToHost);
     };
     std::vector<float> h, h2, h3;
+    const int wmul = c->split_w ? 2 : 1;     // split_weights: every 16-bit weight matrix is [hi | lo], K doubled
     if (!c->w_patch2) {
-        HM_CUDA(c, dev_alloc(c, &c->w_patch2, (size_t)DM * KPATCH));
+        HM_CUDA(c, dev_alloc(c, &c->w_patch2, (size_t)DM * KPATCH * wmul));
         HM_CUDA(c, dev_alloc(c, &c->pos_tab, (size_t)TOK * DM));
         HM_CUDA(c, dev_alloc(c, &c->tok0, (size_t)HD));
         HM_CUDA(c, dev_alloc(c, &c->w_read, (size_t)NREAD * HD));
@@ -717,7 +742,7 @@ int hm_finalize_weights(hm_ctx* c) {
         HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&tmp), w2.size() * 4));
         cudaError_t e1 = cudaMemcpy(tmp, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice);
         f32_to_w16_kernel<<<(unsigned)((w2.size() + 255) / 256), 256>>>(
-            tmp, reinterpret_cast<uint16_t*>(c->w_patch2), w2.size(), (int)c->b_format);
+            tmp, reinterpret_cast<uint16_t*>(c->w_patch2), w2.size(), (int)c->b_format, c->split_w ? 1 : 0, KPATCH);
         cudaError_t e2 = cudaDeviceSynchronize();
         cudaFree(tmp);
         HM_CUDA(c, e1);
@@ -764,12 +789,12 @@ int hm_finalize_weights(hm_ctx* c) {
     }
     // ---- weight tensor maps ------------------------------------------------------------------
     const uint32_t brow = (uint32_t)(c->plan.bn / c->plan.cta_group);
-    bool ok = make_tmap_bf16_2d(&c->tm_wpatch, c->w_patch2, DM, KPATCH, KPATCH, brow);
+    bool ok = make_tmap_bf16_2d(&c->tm_wpatch, c->w_patch2, DM, KPATCH * wmul, KPATCH * wmul, brow);
     for (int i = 0; i < DEPTH && ok; ++i) {
-        ok = make_tmap_bf16_2d(&c->blk[i].tm_qkv, find(c, blk_name(i, "attn.qkv.weight"))->bf16, 3 * DM, DM, DM, brow) &&
-             make_tmap_bf16_2d(&c->blk[i].tm_proj, find(c, blk_name(i, "attn.proj.weight"))->bf16, DM, DM, DM, brow) &&
-             make_tmap_bf16_2d(&c->blk[i].tm_fc1, find(c, blk_name(i, "mlp.fc1.weight"))->bf16, DFF, DM, DM, brow) &&
-             make_tmap_bf16_2d(&c->blk[i].tm_fc2, find(c, blk_name(i, "mlp.fc2.weight"))->bf16, DM, DFF, DFF, brow);
+        ok = make_tmap_bf16_2d(&c->blk[i].tm_qkv, find(c, blk_name(i, "attn.qkv.weight"))->bf16, 3 * DM, DM * wmul, DM * wmul, brow) &&
+             make_tmap_bf16_2d(&c->blk[i].tm_proj, find(c, blk_name(i, "attn.proj.weight"))->bf16, DM, DM * wmul, DM * wmul, brow) &&
+             make_tmap_bf16_2d(&c->blk[i].tm_fc1, find(c, blk_name(i, "mlp.fc1.weight"))->bf16, DFF, DM * wmul, DM * wmul, brow) &&
+             make_tmap_bf16_2d(&c->blk[i].tm_fc2, find(c, blk_name(i, "mlp.fc2.weight"))->bf16, DM, DFF * wmul, DFF * wmul, brow);
     }
     if (!ok) return fail(c, HM_ERR_CUDA, "weight tensor-map encoding failed");
     // ---- cached raw pointers -----------------------------------------------------------------
@@ -992,6 +1017,9 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
         HM_CUDA(c, cudaEventSynchronize(c->crop_event));
         c->crop_event_pending = false;
     }
+    // crop_dev / frame_dev are single context-owned buffers: a call on another stream (pipelined frames) must not
+    // overwrite them while the previous call's crop kernel still reads them (no-op on the same stream)
+    if (c->crop_kernel_recorded) HM_CUDA(c, cudaStreamWaitEvent(s, c->crop_kernel_event, 0));
     double band_lo = (double)H, band_hi = -1.0;   // source rows any crop can read (host frames: only these are uploaded)
     for (int i = 0; i < n; ++i) {
         const double* box = boxes_xyxy + 4 * i;
@@ -1012,7 +1040,7 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
     const uint8_t* frame = frame_bgr;
     if (!frame_on_device) {
         const size_t bytes = (size_t)H * (size_t)row_stride;
-        if (!c->frame_dev || bytes > (size_t)c->cfg.max_frame_bytes)
+        if (!c->frame_dev || bytes - (size_t)(row_stride - (int64_t)W * 3) > (size_t)c->cfg.max_frame_bytes)
             return fail(c, HM_ERR_INVALID, "hm_preprocess: frame larger than hm_config.max_frame_bytes");
         // the warp maps the 256 x 256 patch onto the square [c - size/2, c + size/2]^2 (no rotation) and reads
         // bilinear neighbours: rows outside the union of those windows (+ margin) are never touched
@@ -1028,7 +1056,8 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
             c->crop_rect[i][0] = x0; c->crop_rect[i][1] = x1; c->crop_rect[i][2] = y0; c->crop_rect[i][3] = y1;
             if (x1 >= x0 && y1 >= y0) rect_bytes += (size_t)(x1 - x0 + 1) * 3 * (size_t)(y1 - y0 + 1);
         }
-        const size_t band_bytes = r1 >= r0 ? (size_t)(r1 - r0 + 1) * row_stride : 0;
+        // whole rows except the last one, which ends with its last pixel (the caller's buffer need not hold row padding there)
+        const size_t band_bytes = r1 >= r0 ? (size_t)(r1 - r0) * row_stride + (size_t)W * 3 : 0;
         if (rect_bytes + (size_t)n * 65536 < band_bytes) {       // 64 KB per copy ~ the fixed cost of a pageable 2-D copy
             for (int i = 0; i < n; ++i) {
                 const long x0 = c->crop_rect[i][0], x1 = c->crop_rect[i][1], y0 = c->crop_rect[i][2], y1 = c->crop_rect[i][3];
@@ -1051,6 +1080,8 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
         launch_pdl(crop_warp_normalize_kernel, dim3(256, n), dim3(256), 0, s, frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
     }
     HM_CUDA(c, cudaGetLastError());
+    HM_CUDA(c, cudaEventRecord(c->crop_kernel_event, s));
+    c->crop_kernel_recorded = true;
     return HM_OK;
 }
 

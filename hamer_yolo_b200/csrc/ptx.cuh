@@ -26,6 +26,23 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// fp32 -> fp16 with saturation.  fp16 tops out at 65,504; a plain round-to-nearest conversion turns a
+// larger activation (trained ViT-H blocks have fc1 outliers) or weight into +-inf, which the next GEMM
+// spreads over its whole output row as NaN.  cvt.satfinite clamps to +-65,504 instead (NaN stays NaN)
+// and is the same single F2FP instruction.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint16_t half_bits_sat(float v) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return r;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (no-ops when the kernel was launched without the attribute)
 // ----------------------------------------------------------------------------------------------
 // Every kernel of the hot path calls pdl_prologue() first: it lets the next kernel of the stream start its own

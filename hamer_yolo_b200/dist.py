@@ -79,6 +79,12 @@ def forward_sharded(model, img_all, group=None):
     n = img_all.shape[0]
     lo, hi = shard_range(n, rank, world)
     counts = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
-    out, _ = model({'img': img_all[lo:hi]})
-    rec = all_gather_records(pack_outputs(out), counts, group)
+    if hi > lo:
+        out, _ = model({'img': img_all[lo:hi]})
+        rec_local = pack_outputs(out)
+    else:
+        # fewer hands than ranks (2 hands of a video frame on 8 GPUs): this rank has nothing to run but must still take
+        # part in the collective, with a zero-row record (all_gather_records pads it to the largest shard)
+        rec_local = torch.zeros(0, RECORD_FLOATS, dtype=torch.float32, device=img_all.device)
+    rec = all_gather_records(rec_local, counts, group)
     return unpack_outputs(rec)

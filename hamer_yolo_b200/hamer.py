@@ -35,8 +35,10 @@ class _ManoHandle:
 class Engine:
     """Owns one hm_ctx (one device, one stream user).  Thin: argument marshalling only."""
 
+    MAX_GRAPHS = 8      # cached CUDA graphs (least recently used is dropped): each pins a [B,3,256,256] static input
+
     def __init__(self, device, max_batch=64, max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0,
-                 attention_legacy=0, mano_legacy=0, use_graphs=True, deterministic=0):
+                 attention_legacy=0, mano_legacy=0, use_graphs=True, deterministic=0, split_weights=0):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -47,7 +49,8 @@ class Engine:
         self.max_frame_bytes = int(max_frame_bytes)
         cfg = _lib.HmConfig(max_batch=self.max_batch, max_frame_bytes=self.max_frame_bytes,
                             gemm_cta_group=int(gemm_cta_group), attention_legacy=int(attention_legacy),
-                            mano_legacy=int(mano_legacy), deterministic=int(deterministic))
+                            mano_legacy=int(mano_legacy), deterministic=int(deterministic),
+                            split_weights=int(split_weights))
         h = C.c_void_p()
         rc = self.lib.hm_create(C.byref(h), self.index, C.byref(cfg))
         if rc != 0:
@@ -78,15 +81,24 @@ class Engine:
         return _lib.check(self.h, rc)
 
     # -- weights / MANO --------------------------------------------------------------------------
+    def _drop_graphs(self):
+        """Captured graphs hold weight / MANO table pointers and tensor maps by value: any reload invalidates them."""
+        if self._graphs:
+            torch.cuda.synchronize(self.device)
+            self._graphs = {}
+
     def set_weight(self, name, tensor):
+        self._drop_graphs()
         t = tensor.detach().to('cpu', torch.float32).contiguous()
         shape = (C.c_int64 * t.dim())(*t.shape)
         self.check(self.lib.hm_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
 
     def finalize_weights(self):
+        self._drop_graphs()
         self.check(self.lib.hm_finalize_weights(self.h))
 
     def set_mano(self, m):
+        self._drop_graphs()
         arr = lambda k, dt: np.ascontiguousarray(m[k], dtype=dt)
         keep = [arr('v_template', np.float32), arr('shapedirs', np.float32), arr('posedirs', np.float32),
                 arr('J_regressor', np.float32), arr('lbs_weights', np.float32), arr('parents', np.int32),
@@ -128,7 +140,7 @@ class Engine:
 
     def _forward_graph(self, img):
         B = img.shape[0]
-        g = self._graphs.get(B)
+        g = self._graphs.pop(B, None)
         if g is None:
             per = sum(int(np.prod(shp)) for _, shp in self._FIELDS)
             static_img = torch.empty(B, 3, IMG, IMG, device=self.device, dtype=torch.float32)
@@ -145,7 +157,11 @@ class Engine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.check(self.lib.hm_forward(self.h, _ptr(static_img), B, C.byref(s), self.stream()))
-            g = self._graphs[B] = (graph, static_img, static_flat)
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                torch.cuda.synchronize(self.device)
+                self._graphs.pop(next(iter(self._graphs)))      # dicts keep insertion order: first = least recently used
+            g = (graph, static_img, static_flat)
+        self._graphs[B] = g                                    # (re-)insert at the most-recently-used end
         graph, static_img, static_flat = g
         static_img.copy_(img)
         graph.replay()
@@ -154,6 +170,8 @@ class Engine:
     def forward(self, img, want_feats=False):
         """img: CUDA float32 [B,3,256,256].  Returns dict of CUDA tensors (hm_outputs fields)."""
         B = img.shape[0]
+        if B == 0:                                             # an empty shard (fewer hands than ranks): empty tensors, no launch
+            return self._outputs(0, want_feats)
         if (self.use_graphs and not want_feats and not self._profiling and B <= self.max_batch
                 and not torch.cuda.is_current_stream_capturing()):
             with torch.cuda.device(self.device):
@@ -257,12 +275,13 @@ class HAMER:
     dicts as hamer.py:124-156; tensors live on the model's CUDA device, float32."""
 
     def __init__(self, cfg=None, init_renderer=False, mano=None, device='cuda:0', max_batch=64,
-                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0, use_graphs=True, deterministic=False):
+                 max_frame_bytes=1920 * 1080 * 3, gemm_cta_group=0, use_graphs=True, deterministic=False,
+                 split_weights=False):
         self.cfg = cfg if cfg is not None else default_config()
         if self.cfg.MODEL.IMAGE_SIZE != 256:
             raise AssertionError(f'MODEL.IMAGE_SIZE ({self.cfg.MODEL.IMAGE_SIZE}) should be 256 for ViT backbone')
         self.engine = Engine(device, max_batch, max_frame_bytes, gemm_cta_group, use_graphs=use_graphs,
-                             deterministic=int(deterministic))
+                             deterministic=int(deterministic), split_weights=int(split_weights))
         self.device = self.engine.device
         self.training = False
         if mano is None:
@@ -317,9 +336,9 @@ class HAMER:
             'pred_mano_params': {k: v.clone() for k, v in pred_mano_params.items()},   # hamer.py:126
             'pred_cam_t': t['pred_cam_t'],
             'focal_length': t['focal_length'],
-            'pred_keypoints_3d': t['pred_keypoints_3d'].reshape(B, -1, 3),
-            'pred_vertices': t['pred_vertices'].reshape(B, -1, 3),
-            'pred_keypoints_2d': t['pred_keypoints_2d'].reshape(B, -1, 2),
+            'pred_keypoints_3d': t['pred_keypoints_3d'].reshape(B, 21, 3),
+            'pred_vertices': t['pred_vertices'].reshape(B, 778, 3),
+            'pred_keypoints_2d': t['pred_keypoints_2d'].reshape(B, 21, 2),
         }
         pred_mano_params['trans'] = t['pred_cam_t']                                     # hamer.py:155
         return output, pred_mano_params
@@ -331,16 +350,19 @@ class HAMER:
 
 
 def load_hamer(checkpoint_path=None, mano=None, device='cuda:0', max_batch=64, cfg=None, state_dict=None,
-               deterministic=False):
+               deterministic=False, split_weights=False):
     """load_hamer (models/__init__.py:32-47): returns (model, model_cfg).  ``checkpoint_path`` is a
     Lightning checkpoint ({'state_dict': ...}) or a plain state dict saved with torch.save;
     ``state_dict`` can be passed directly instead.  ``deterministic=True`` fixes the fp32 summation order of the
-    residual GEMMs (bit-identical results across runs and batch sizes, a few percent slower)."""
+    residual GEMMs (bit-identical results across runs and batch sizes, a few percent slower).
+    ``split_weights=True`` keeps the backbone weights as fp16 hi + lo pairs (fp32-faithful weights for checkpoints whose
+    values are not fp16-representable - a trained HaMeR checkpoint - at twice the tensor-core work)."""
     cfg = cfg if cfg is not None else default_config()
     if cfg.MODEL.BACKBONE.TYPE == 'vit' and 'BBOX_SHAPE' not in cfg.MODEL:
         assert cfg.MODEL.IMAGE_SIZE == 256
         cfg.MODEL.BBOX_SHAPE = [192, 256]
-    model = HAMER(cfg, mano=mano, device=device, max_batch=max_batch, deterministic=deterministic)
+    model = HAMER(cfg, mano=mano, device=device, max_batch=max_batch, deterministic=deterministic,
+                  split_weights=split_weights)
     if state_dict is None:
         if checkpoint_path is None:
             raise ValueError('load_hamer needs checkpoint_path or state_dict')

@@ -45,7 +45,12 @@ typedef struct hm_config {
     int32_t deterministic;    /* 1 = never split the K dimension of the residual GEMMs: fixed fp32 summation order, results
                                  bit-identical across runs and batch sizes (default 0: the partial-wave tiles are split
                                  into K-slices that are reduce-added in arrival order - last-bit differences) */
-    int32_t reserved[2];
+    int32_t split_weights;    /* 1 = the backbone weight matrices are kept as W_hi + W_lo (two fp16 matrices, ~21 mantissa
+                                 bits) and every backbone GEMM runs over K' = 2K: an arbitrary fp32 checkpoint then meets the
+                                 1e-3 parameter bar with the margin of fp16-representable weights, at twice the tensor-core
+                                 work (default 0: weights rounded once to fp16).  Must be chosen before
+                                 the first hm_set_weight. */
+    int32_t reserved[1];
 } hm_config;
 
 /* Device pointers of the tensors HAMER.forward_step returns (hamer/hamer/models/hamer.py:124-156).

@@ -153,6 +153,59 @@ def test_allgather_world2_gloo(tmp_path, n):
         assert p.returncode == 0, out.decode()[-2000:]
 
 
+_GLOO_SHARDED_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hamer_yolo_b200 import dist as hd
+dist.init_process_group('gloo', init_method='env://')
+rank, world = dist.get_rank(), dist.get_world_size()
+n = int(sys.argv[2])
+
+def fake_model(batch):
+    """Stands in for HAMER.forward on CPU: every output is a function of the crop's first pixel; like hm_forward it
+    rejects an empty batch."""
+    x = batch['img']
+    B = x.shape[0]
+    if B == 0:
+        raise RuntimeError('batch size must be positive')
+    v = x[:, 0, 0, 0]
+    f = lambda *s: v.reshape(B, *([1] * len(s))).expand(B, *s).clone()
+    out = {'pred_vertices': f(778, 3), 'pred_keypoints_3d': f(21, 3) + 1, 'pred_keypoints_2d': f(21, 2) + 2,
+           'pred_cam': f(3) + 3, 'pred_cam_t': f(3) + 4,
+           'pred_mano_params': {'global_orient': f(1, 3, 3) + 5, 'hand_pose': f(15, 3, 3) + 6, 'betas': f(10) + 7}}
+    return out, None
+
+img = torch.arange(n, dtype=torch.float32).reshape(n, 1, 1, 1).expand(n, 3, 4, 4).contiguous()
+got = hd.forward_sharded(fake_model, img)
+want, _ = fake_model({'img': img})
+assert got['pred_vertices'].shape == (n, 778, 3)
+for k in ('pred_vertices', 'pred_keypoints_3d', 'pred_keypoints_2d', 'pred_cam', 'pred_cam_t'):
+    assert torch.equal(got[k], want[k]), k
+for k in ('global_orient', 'hand_pose', 'betas'):
+    assert torch.equal(got['pred_mano_params'][k], want['pred_mano_params'][k]), k
+dist.barrier()
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+@pytest.mark.parametrize('n', [1, 5])
+def test_forward_sharded_world2_gloo(tmp_path, n):
+    """forward_sharded on two gloo ranks; n = 1 leaves rank 1 with an empty shard (fewer hands than ranks): it must
+    skip the model call and still join the all-gather instead of raising while rank 0 blocks."""
+    script = tmp_path / 'ws.py'
+    script.write_text(_GLOO_SHARDED_WORKER)
+    port = 30100 + (os.getpid() % 500) + n
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(n)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()[-2000:]
+
+
 def test_npy_record_layout(tmp_path):
     """infer.py:1296-1312 layout, written and read back the way infer.py:1350 reads it."""
     pytest.importorskip('cv2')

@@ -41,9 +41,13 @@ def oracle_out(oracle_model, seeded_images):
 # ---------------------------------------------------------------------------------------------
 # building blocks
 # ---------------------------------------------------------------------------------------------
+# The last three shapes are the batch-64 step's own schedules (M = 64 x 192 = 12288 rows, CTA-pair 256 x 256 tiles):
+# N = 1280 gives 240 tiles for 74 CTA pairs = 222 whole tiles + 18 tail tiles split into K-slices (gemm_host.cuh),
+# N = 3840 / 5120 the plain multi-wave persistent loop.
 @pytest.mark.parametrize('cta_group', [2, 1])
 @pytest.mark.parametrize('epi,M,N,K', [(0, 192, 3840, 1280), (1, 384, 5120, 1280), (2, 200, 1280, 5120),
-                                       (3, 192, 1280, 1536), (2, 1536, 1280, 1280)])
+                                       (3, 192, 1280, 1536), (2, 1536, 1280, 1280),
+                                       (2, 12288, 1280, 1280), (2, 12288, 1280, 5120), (1, 12288, 5120, 1280)])
 def test_gemm_epilogues(engine, cta_group, epi, M, N, K):
     dev = engine.device
     g = torch.Generator(device=dev).manual_seed(M + N + K + epi)
@@ -67,6 +71,35 @@ def test_gemm_epilogues(engine, cta_group, epi, M, N, K):
         assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3)
     else:
         assert torch.allclose(out, ref, rtol=1e-4, atol=2e-4)
+
+
+def test_fp16_conversions_saturate(engine):
+    """Activations above the fp16 range (65,504) must clamp, not become inf: GEMM epilogues (bias, GELU) and the
+    LayerNorm output."""
+    dev = engine.device
+    g = torch.Generator(device=dev).manual_seed(77)
+    M, N, K = 256, 256, 1280
+    A = (torch.randn(M, K, generator=g, device=dev) * 100).half()
+    W = (torch.randn(N, K, generator=g, device=dev) * 10).half()
+    bias = torch.randn(N, generator=g, device=dev)
+    acc = A.float() @ W.float().t() + bias
+    assert (acc.abs() > 65504).float().mean().item() > 0.01          # the case is live
+    for epi in (0, 1):
+        out = torch.zeros(M, N, device=dev, dtype=torch.float16)
+        engine.check(engine.lib.hm_test_gemm(engine.h, 2, 256, epi, 0, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
+                                             C.c_void_p(bias.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                             C.c_void_p(out.data_ptr()), M, N, K, engine.stream()))
+        ref = (torch.nn.functional.gelu(acc) if epi == 1 else acc).clamp(-65504, 65504)
+        assert torch.isfinite(out).all()
+        assert torch.allclose(out.float(), ref, rtol=2e-3, atol=32.0)     # one fp16 ulp at 32768..65504 is 32
+    x = torch.randn(64, 1280, generator=g, device=dev)
+    gamma = torch.full((1280,), 1e5, device=dev)
+    beta = torch.zeros(1280, device=dev)
+    y = torch.empty(64, 1280, device=dev, dtype=torch.float16)
+    engine.check(engine.lib.hm_test_layernorm(engine.h, C.c_void_p(x.data_ptr()), C.c_void_p(gamma.data_ptr()),
+                                              C.c_void_p(beta.data_ptr()), C.c_void_p(y.data_ptr()), 64, 1e-6, 1, engine.stream()))
+    ref = torch.nn.functional.layer_norm(x, (1280,), gamma, beta, 1e-6).clamp(-65504, 65504)
+    assert torch.isfinite(y).all() and torch.allclose(y.float(), ref, rtol=2e-3, atol=1.0)
 
 
 @pytest.mark.parametrize('rows,f16', [(192, 1), (1000, 1), (192, 0)])
@@ -161,6 +194,37 @@ def test_crop_edge_cases(engine):
         engine.preprocess(frame, [[10., 10., 10., 50.]], [True])      # empty box
 
 
+def test_crop_rectangle_upload_branch(engine):
+    """A 1080p host frame with a few small, scattered boxes: hm_preprocess uploads one rectangle per crop instead of the
+    row band (the rectangles + 64 KB each are much smaller than the band).  The device frame buffer is first filled
+    with a different frame, so a pixel read outside the uploaded rectangles would show."""
+    from oracle import crop as oc
+    other = np.full((1080, 1920, 3), 255, np.uint8)
+    engine.preprocess(other, [[0., 0., 1920., 1080.]], [True])            # band path: the whole poison frame is resident
+    frame = synthetic_frame(1080, 1920, 21)
+    cases = [['right', [100., 60., 180., 150.]], ['left', [1700., 900., 1790., 1000.]], ['right', [905.5, 500.25, 990., 590.75]],
+             ['left', [1880., 20., 1960., 100.]]]                          # the last one hangs over the right edge
+    boxes = [c[1] for c in cases]
+    # the branch condition of hm_api.cu (hm_preprocess), restated: rectangles (+4 px margin) + 64 KB each < row band
+    rect = 0
+    lo, hi = 1e9, -1e9
+    for b in boxes:
+        cx, cy, s = oc.box_to_center_size(*b)
+        x0, x1 = max(0, np.floor(cx - s / 2) - 4), min(1919, np.ceil(cx + s / 2) + 4)
+        y0, y1 = max(0, np.floor(cy - s / 2) - 4), min(1079, np.ceil(cy + s / 2) + 4)
+        rect += (x1 - x0 + 1) * 3 * (y1 - y0 + 1)
+        lo, hi = min(lo, cy - s / 2), max(hi, cy + s / 2)
+    band = (min(1079, np.ceil(hi) + 4) - max(0, np.floor(lo) - 4)) * 1920 * 3
+    assert rect + len(boxes) * 65536 < band
+    img, center, size, trans = engine.preprocess(frame, boxes, [c[0] == 'right' for c in cases])
+    ref = oc.prepare_batch_bbox(frame, cases)
+    assert np.array_equal(img.cpu().numpy(), ref['img'])
+    assert np.array_equal(center, ref['box_center']) and np.array_equal(size, ref['box_size'])
+    # same frame through the band path (one box spanning the frame forces it) gives the same crops
+    img2, *_ = engine.preprocess(frame, boxes + [[0., 0., 1920., 1080.]], [c[0] == 'right' for c in cases] + [True])
+    assert torch.equal(img2[:4], img)
+
+
 # ---------------------------------------------------------------------------------------------
 # MANO layer
 # ---------------------------------------------------------------------------------------------
@@ -241,6 +305,13 @@ def test_mano_lbs_full_size_properties(engine):
     v_s, j_s = engine.mano_lbs(betas[idx].to(dev), rot[idx].to(dev))
     assert torch.equal(verts[idx.to(dev)], v_s) and torch.equal(joints[idx.to(dev)], j_s)
     assert torch.isfinite(verts).all()
+    # a random 256-hand subset of the full-size run against the oracle
+    from oracle.mano import mano_forward
+    from hamer_yolo_b200.mano_data import synthetic_mano
+    sub = torch.randperm(B, generator=torch.Generator().manual_seed(3))[:256]
+    v_ref, j_ref = mano_forward(rot[sub, :1], rot[sub, 1:], betas[sub], synthetic_mano(0))
+    assert (verts[sub.to(dev)].cpu() - v_ref).norm(dim=-1).max().item() < 0.03 * MM
+    assert (joints[sub.to(dev)].cpu() - j_ref).norm(dim=-1).max().item() < 0.02 * MM
     from oracle.head import rot6d_to_rotmat
     Q = rot6d_to_rotmat(torch.randn(B, 6, generator=torch.Generator().manual_seed(9)))
     rot2 = rot.clone()
