@@ -12,14 +12,17 @@ from .configs import CfgNode, default_config
 from .mano_data import load_mano_pkl, synthetic_mano
 
 __all__ = ['CfgNode', 'default_config', 'load_mano_pkl', 'synthetic_mano', 'HAMER', 'load_hamer',
-           'hamer_inference', 'Engine']
+           'hamer_inference', 'Engine', 'HAMER_INFER', 'ViTDetDataset']
 
 
 def __getattr__(name):
     # torch / the CUDA library are imported lazily so that config + data helpers work without them
-    if name in ('HAMER', 'load_hamer', 'Engine'):
+    if name in ('HAMER', 'load_hamer', 'Engine', 'HAMER_INFER'):
         from . import hamer
         return getattr(hamer, name)
+    if name == 'ViTDetDataset':
+        from .datasets import ViTDetDataset
+        return ViTDetDataset
     if name == 'hamer_inference':
         from .inference import hamer_inference
         return hamer_inference

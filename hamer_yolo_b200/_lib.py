@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libhamer_b200.so')
+LIB_PATH = os.environ.get('HAMER_B200_LIB') or os.path.join(_HERE, 'libhamer_b200.so')   # (the override is for A/B builds)
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -31,9 +31,9 @@ class HmError(RuntimeError):
 
 # every symbol include/hamer_b200.h declares (tests check the library exports all of them)
 EXPORTS = ('hm_create', 'hm_destroy', 'hm_last_error', 'hm_set_weight', 'hm_finalize_weights',
-           'hm_set_mano', 'hm_preprocess', 'hm_forward', 'hm_backbone', 'hm_mano_head',
-           'hm_mano_lbs', 'hm_camera_postprocess', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
-           'hm_profile_collect', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention')
+           'hm_set_mano', 'hm_preprocess', 'hm_preprocess_centers', 'hm_forward', 'hm_backbone', 'hm_mano_head',
+           'hm_mano_lbs', 'hm_camera_postprocess', 'hm_comm_unique_id', 'hm_comm_init', 'hm_comm_destroy', 'hm_allgather', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
+           'hm_profile_collect', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention', 'hm_test_mano_clocks')
 
 PROFILE_CATEGORIES = ('im2col', 'gemm_patch', 'layernorm', 'gemm_qkv', 'attention', 'gemm_proj',
                       'gemm_fc1', 'gemm_fc2', 'head', 'mano_lbs', 'crop')
@@ -60,17 +60,23 @@ def load():
     lib.hm_finalize_weights.argtypes = [vp]
     lib.hm_set_mano.argtypes = [vp] + [vp] * 8
     lib.hm_preprocess.argtypes = [vp, vp, i32, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.hm_preprocess_centers.argtypes = [vp, vp, i32, i32, i64, i32, vp, vp, i32, vp, vp, vp]
     lib.hm_forward.argtypes = [vp, vp, i32, C.POINTER(HmOutputs), vp]
     lib.hm_backbone.argtypes = [vp, vp, i32, vp, vp]
     lib.hm_mano_head.argtypes = [vp, vp, i32, C.POINTER(HmOutputs), vp]
     lib.hm_mano_lbs.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.hm_camera_postprocess.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.hm_comm_unique_id.argtypes = [vp]
+    lib.hm_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.hm_comm_destroy.argtypes = [vp]
+    lib.hm_allgather.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.hm_forward_launch_count.argtypes = [vp]
     lib.hm_version.argtypes = []
     lib.hm_version.restype = C.c_char_p
     lib.hm_profile_enable.argtypes = [vp, i32]
     lib.hm_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32), i32]
     lib.hm_test_gemm.argtypes =[vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.hm_test_mano_clocks.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, vp]
     lib.hm_test_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, i32, vp]
     lib.hm_test_attention.argtypes = [vp, i32, vp, vp, i32, vp]
     for name in EXPORTS:

@@ -23,7 +23,9 @@ namespace hm {
 
 struct CropParams {
     double m[6];      // inverse affine (dst -> src), as cv::warpAffine derives it from M
-    int32_t flip;     // 1 = left hand: mirror the patch horizontally
+    int32_t flip;     // 1 = left hand: mirror the patch horizontally (infer.py:229-230); 2 = sample the horizontally
+                      // mirrored frame instead (generate_image_patch_cv2 do_flip, datasets/utils.py:347-349: the
+                      // affine is built for c_x' = W - c_x - 1 and source column x is frame column W - 1 - x)
     int32_t pad;
 };
 
@@ -62,15 +64,15 @@ crop_warp_normalize_kernel(const uint8_t* __restrict__ frame, int H, int W, int6
         const uint8_t* rowp = frame + (size_t)yy * row_stride;
         const int wl = dy ? w10 : w00, wr = dy ? w11 : w01;
         if (x0in) {
-            const uint8_t* q = rowp + (size_t)sx * 3;
+            const uint8_t* q = rowp + (size_t)(p.flip == 2 ? W - 1 - sx : sx) * 3;
             acc[0] += wl * q[0]; acc[1] += wl * q[1]; acc[2] += wl * q[2];
         }
         if (x1in) {
-            const uint8_t* q = rowp + (size_t)(sx + 1) * 3;
+            const uint8_t* q = rowp + (size_t)(p.flip == 2 ? W - 2 - sx : sx + 1) * 3;
             acc[0] += wr * q[0]; acc[1] += wr * q[1]; acc[2] += wr * q[2];
         }
     }
-    const int xo = p.flip ? (255 - x) : x;
+    const int xo = p.flip == 1 ? (255 - x) : x;
     float* o = out + (size_t)n * 3 * 65536 + (size_t)y * 256 + xo;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {                        // c = BGR index; output plane = 2 - c

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.cuh"
 #include "attention.cuh"
 #include "attention_tc5.cuh"
 #include "crop_warp.cuh"
@@ -36,7 +37,6 @@ constexpr int HD = 1024;       // decoder width
 constexpr int HDEPTH = 6;
 constexpr int NREAD = 109;     // 96 pose6d + 10 betas + 3 cam
 constexpr int MANO_CHUNK = 8192;  // legacy 3-kernel path: hands per pass (80 MB of fp32 v_posed stays inside the 126 MB L2)
-constexpr int MANO_FCHUNK = 65536; // fused path: hands per launch (71 MB of coefficient / transform workspace)
 
 std::string g_create_error;
 
@@ -129,11 +129,12 @@ struct hm_ctx {
     __half* m_coef = nullptr;     // [MANO_CHUNK, 320]
     float *m_vposed = nullptr, *m_A = nullptr, *m_jpos = nullptr;
     CUtensorMap tm_mcoef, tm_mbasis;
-    __half* mf_coef = nullptr;    // [MANO_FCHUNK, 160]
-    float* mf_Au = nullptr;       // [MANO_FCHUNK/128][16][128][12]
     CUtensorMap tm_fbasis;
-    bool mano_fused_ok = false;   // joint_map is a permutation (every source joint has exactly one slot)
+    ManoChainConst mano_chain{};  // folded joint regressor + output slots: constant-bank parameter of the fused kernel
+    bool mano_fused_ok = false;   // the fused kernel applies: joint_map is a permutation (every source joint has exactly one
+                                  // slot), the kinematic tree is the standard MANO one, no vertex group needs > 16 joints
     bool mano_legacy = false;
+    long long* mano_clk = nullptr;   // phase-clock buffer of the fused kernel (hm_test_mano_clocks), null in normal use
 
     // preprocess
     uint8_t* frame_dev = nullptr;
@@ -148,6 +149,10 @@ struct hm_ctx {
     bool crop_kernel_recorded = false;
 
     std::vector<void*> allocs;
+
+    // the context's own NCCL communicator (hm_comm_init), one rank per context / GPU
+    ncclComm_t comm = nullptr;
+    int comm_ranks = 0;
 
     // optional per-category timing (hm_profile_*): CUDA events recorded on the launch stream
     bool prof_on = false;
@@ -268,14 +273,8 @@ void lu_solve6(double A[6][6], double b[6]) {
     }
 }
 
-void box_to_affine(const double* box, double* cx_out, double* cy_out, double* size_out, double M[6]) {
-    const double x1 = box[0], y1 = box[1], x2 = box[2], y2 = box[3];
-    const double cx = (x1 + x2) / 2.0, cy = (y1 + y2) / 2.0;               // infer.py:182-183
-    const double w = (2.5 * (x2 - x1) / 200.0) * 200, h = (2.5 * (y2 - y1) / 200.0) * 200;  // :193-199
-    double w_new, h_new;                                                    // expand_to_aspect_ratio
-    if (h / w < 256.0 / 192.0) { h_new = fmax(w * 256 / 192, h); w_new = w; }
-    else { h_new = h; w_new = fmax(h * 192 / 256, w); }
-    const double size = fmax(w_new, h_new);
+// gen_trans_from_patch_cv for a square window of `size` pixels around (cx, cy): 256 x 256 patch, rot = 0, scale = 1
+void center_to_affine(double cx, double cy, double size, double M[6]) {
     const float half = (float)(size * 0.5);
     const float s0x = (float)cx, s0y = (float)cy;
     const float s1x = (float)(cx + 0.0), s1y = (float)(cy + (double)half);
@@ -290,7 +289,17 @@ void box_to_affine(const double* box, double* cx_out, double* cy_out, double* si
     }
     lu_solve6(A, b);
     for (int i = 0; i < 6; ++i) M[i] = b[i];
-    *cx_out = cx; *cy_out = cy; *size_out = size;
+}
+
+// box -> centre and side of the square crop window (infer.py:182-199, datasets/utils.py:15-34 expand_to_aspect_ratio)
+void box_to_center_size(const double* box, double* cx_out, double* cy_out, double* size_out) {
+    const double x1 = box[0], y1 = box[1], x2 = box[2], y2 = box[3];
+    const double cx = (x1 + x2) / 2.0, cy = (y1 + y2) / 2.0;               // infer.py:182-183
+    const double w = (2.5 * (x2 - x1) / 200.0) * 200, h = (2.5 * (y2 - y1) / 200.0) * 200;  // :193-199
+    double w_new, h_new;                                                    // expand_to_aspect_ratio
+    if (h / w < 256.0 / 192.0) { h_new = fmax(w * 256 / 192, h); w_new = w; }
+    else { h_new = h; w_new = fmax(h * 192 / 256, w); }
+    *cx_out = cx; *cy_out = cy; *size_out = fmax(w_new, h_new);
 }
 
 // cv::warpAffine's inversion of M (no WARP_INVERSE_MAP)
@@ -423,55 +432,52 @@ int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaS
     return HM_OK;
 }
 
-// Work units per 256-hand tile for the fused kernel: more units fill the GPU at small B and trim the
-// last wave at large B; each unit re-loads the tile's coefficients / transforms (cost ~1.5 coordinate tiles).
-int mano_pick_split(int pair_tiles, int workers) {
-    int best = 1;
+// Work list of the fused kernel: the pair tiles (256 hands) of the full waves are one unit each; the tiles of the partial
+// last wave are cut into n_split pieces (each repeats the tile's prologue, cost ~4 coordinate tiles) so that the wave
+// ends together.  With fewer tiles than workers every tile is split (small batches).
+void mano_plan(int pair_tiles, int workers, int* whole, int* n_split) {
+    static const int forced = [] { const char* e = getenv("HM_MANO_SPLIT"); return e ? atoi(e) : 0; }();
+    const int tail = pair_tiles % workers;
+    *whole = pair_tiles - tail;
+    *n_split = 1;
+    if (tail == 0) return;
+    if (forced >= 1 && forced <= MF_NT) { *n_split = forced; return; }
     double best_cost = 1e30;
     for (int ns = 1; ns <= MF_NT; ++ns) {
-        const int waves = (pair_tiles * ns + workers - 1) / workers;
-        const double cost = waves * ((MF_NT + ns - 1) / ns + 1.5);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+        const int waves = (tail * ns + workers - 1) / workers;
+        const double cost = waves * ((MF_NT + ns - 1) / ns + 4.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; *n_split = ns; }
     }
-    return best;
 }
 
 int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
                    float* verts, float* joints, float* kp2d, cudaStream_t s) {
     const bool proj = cam_t != nullptr && kp2d != nullptr;
-    for (int lo = 0; lo < B; lo += MANO_FCHUNK) {
-        const int n = (B - lo < MANO_FCHUNK) ? (B - lo) : MANO_FCHUNK;
-        ManoPrepArgs pa{};
-        pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
-        pa.coef = c->mf_coef; pa.A = c->mf_Au; pa.jpos = nullptr; pa.B = n;
-        pa.joints = joints + (size_t)lo * 63;
-        pa.kp2d = proj ? kp2d + (size_t)lo * 42 : nullptr;
-        pa.cam_t = proj ? cam_t + (size_t)lo * 3 : nullptr;
-        pa.focal_over_size = 5000.0f / 256.0f;
-        launch_pdl(mano_prep_kernel<true>, dim3((n + 7) / 8), dim3(128), 0, s, c->mano, pa);
-        ManoFusedArgs a{};
-        a.coef = c->mf_coef; a.Au = c->mf_Au; a.cam_t = pa.cam_t; a.verts = verts + (size_t)lo * MANO_V * 3;
-        a.joints = pa.joints; a.kp2d = pa.kp2d; a.focal_over_size = pa.focal_over_size; a.B = n;
-        const int pair_tiles = (n + 2 * MF_BM - 1) / (2 * MF_BM);
-        const int workers_max = c->num_sms / 2;
-        a.n_split = mano_pick_split(pair_tiles, workers_max);
-        static const int mano_dbg = [] { const char* e = getenv("HM_MANO_DBG"); return e ? atoi(e) : 0; }();
-        a.dbg = mano_dbg;   // kernel ablation switches for profiling (see ManoFusedArgs::dbg); 0 in normal use
-        const int units = pair_tiles * a.n_split;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * (units < workers_max ? units : workers_max));
-        cfg.blockDim = dim3(MF_THREADS);
-        cfg.dynamicSmemBytes = MF_SMEM_BYTES;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        HM_CUDA(c, cudaLaunchKernelEx(&cfg, mano_fused_kernel, c->tm_fbasis, c->mano, a));
-    }
+    ManoFusedArgs a{};
+    a.betas = betas; a.rotmats = rotmats; a.cam_t = proj ? cam_t : nullptr;
+    a.verts = verts; a.joints = joints; a.kp2d = proj ? kp2d : nullptr;
+    a.focal_over_size = 5000.0f / 256.0f;
+    a.B = B;
+    const int pair_tiles = (B + 2 * MF_BM - 1) / (2 * MF_BM);
+    const int workers_max = c->num_sms / 2;
+    mano_plan(pair_tiles, workers_max, &a.whole, &a.n_split);
+    static const int mano_dbg = [] { const char* e = getenv("HM_MANO_DBG"); return e ? atoi(e) : 0; }();
+    a.dbg = mano_dbg;   // kernel ablation switches for profiling (see ManoFusedArgs::dbg); 0 in normal use
+    a.clk = c->mano_clk;
+    const int units = a.whole + (pair_tiles - a.whole) * a.n_split;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (units < workers_max ? units : workers_max));
+    cfg.blockDim = dim3(MF_THREADS);
+    cfg.dynamicSmemBytes = MF_SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    HM_CUDA(c, cudaLaunchKernelEx(&cfg, mano_fused_kernel, c->tm_fbasis, c->mano_chain, c->mano.fz_tab, a));
     HM_CUDA(c, cudaGetLastError());
     return HM_OK;
 }
@@ -479,15 +485,16 @@ int lbs_fused_impl(hm_ctx* c, const float* betas, const float* rotmats, const fl
 int lbs_impl(hm_ctx* c, const float* betas, const float* rotmats, const float* cam_t, int B,
              float* verts, float* joints, float* kp2d, cudaStream_t s) {
     ProfScope ps(c, s, PC_MANO_LBS);
-    // the fused kernel stores vertices with 8-byte vector stores
-    if (c->mano_fused_ok && !c->mano_legacy && (reinterpret_cast<uintptr_t>(verts) & 7u) == 0)
+    // the fused kernel fetches betas / rotations with 16-byte granular bulk copies and stores vertices 8 bytes per lane
+    if (c->mano_fused_ok && !c->mano_legacy && (reinterpret_cast<uintptr_t>(verts) & 7u) == 0 &&
+        (reinterpret_cast<uintptr_t>(rotmats) & 15u) == 0 && (reinterpret_cast<uintptr_t>(betas) & 15u) == 0)
         return lbs_fused_impl(c, betas, rotmats, cam_t, B, verts, joints, kp2d, s);
     for (int lo = 0; lo < B; lo += MANO_CHUNK) {                 // chunk: v_posed stays L2-resident
         const int n = (B - lo < MANO_CHUNK) ? (B - lo) : MANO_CHUNK;
         ManoPrepArgs pa{};
         pa.betas = betas + (size_t)lo * 10; pa.rotmats = rotmats + (size_t)lo * 144;
         pa.coef = c->m_coef; pa.A = c->m_A; pa.jpos = c->m_jpos; pa.B = n;
-        launch_pdl(mano_prep_kernel<false>, dim3((n + 7) / 8), dim3(128), 0, s, c->mano, pa);
+        launch_pdl(mano_prep_kernel, dim3((n + 7) / 8), dim3(128), 0, s, c->mano, pa);
         GemmParams p{};
         p.M = n; p.N = MANO_NPAD; p.K = MANO_KTOT; p.bias = c->mano.template_n; p.out = c->m_vposed;
         p.ldo = MANO_NPAD; p.pos = c->mano.zero_row; p.pos_rows = 1; p.b_format = 0;
@@ -629,6 +636,7 @@ void hm_destroy(hm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
     for (void* p : c->allocs) cudaFree(p);
     for (void* p : c->mano_allocs) cudaFree(p);
     for (auto& kv : c->w) { cudaFree(kv.second.f32); cudaFree(kv.second.bf16); }
@@ -855,17 +863,20 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
                 basis16[(size_t)n * MANO_KTOT + MANO_KB + k] = lo;
             }
         }
-    // fused kernel: same basis with the rows of each 16-vertex group ordered (x0 x1 y0 y1 z0 z1) per vertex pair,
-    // so that the accumulator columns a thread reads are packed pairs for FFMA2
+    // fused kernel: same basis with the rows of each vertex group ordered (x0 x1 y0 y1 z0 z1) per vertex pair, so that the
+    // accumulator columns a thread reads are packed pairs for FFMA2; K = [shape hi | pose | shape lo | template hi | lo | 0 0 0]
     std::vector<__half> basis16f((size_t)MANO_NPAD * MANO_KB, __float2half(0.f));
     for (int v = 0; v < MANO_V; ++v)
         for (int cdim = 0; cdim < 3; ++cdim) {
-            const int i = v % MF_GV;
-            const size_t nf = (size_t)(v / MF_GV) * MF_GCOLS + 6 * (i >> 1) + 2 * cdim + (i & 1);
+            const int i = v % MF_VPT;
+            const size_t nf = (size_t)(v / MF_VPT) * MF_GCOLS + 6 * (i >> 1) + 2 * cdim + (i & 1);
             const __half* src = &basis16[(size_t)(v * 3 + cdim) * MANO_KTOT];
             __half* dst = &basis16f[nf * MANO_KB];
             for (int k = 0; k < 145; ++k) dst[k] = src[k];                     // shape hi | pose (fp16-rounded)
             for (int k = 0; k < 10; ++k) dst[145 + k] = src[MANO_KB + k];      // shape lo, multiplied by the repeated betas
+            const float t = v_template[v * 3 + cdim];
+            dst[MF_K_TMPL] = __float2half_rn(t);                               // template hi / lo, coefficient 1
+            dst[MF_K_TMPL + 1] = __float2half_rn(t - __half2float(dst[MF_K_TMPL]));
         }
     // folded joint regressor (double accumulation; one-time)
     std::vector<float> jt(48), js(480);
@@ -909,32 +920,32 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
             }
         wnu[w] = nu;
     }
-    // fused kernel: union of joints + weights per 16-vertex group (warp-uniform in the epilogue)
-    std::vector<float> ftab((size_t)MF_GROUPS * MF_TAB_F4 * 4, 0.f);
-    for (int g = 0; g < MF_GROUPS; ++g) {
-        float* tab = ftab.data() + (size_t)g * MF_TAB_F4 * 4;
+    // fused kernel: union of joints + weights per vertex group (warp-uniform in the epilogue); layout at MF_TAB_STRIDE
+    std::vector<float> ftab((size_t)MF_LIVE_GROUPS * MF_TAB_STRIDE / 4, 0.f);
+    bool union_fits = true;
+    for (int g = 0; g < MF_LIVE_GROUPS; ++g) {
+        float* tab = ftab.data() + (size_t)g * MF_TAB_STRIDE / 4;
         int32_t* tabi = reinterpret_cast<int32_t*>(tab);
         uint32_t um = 0;
-        for (int i = 0; i < MF_GV; ++i) {
-            const int v = g * MF_GV + i;
-            if (v >= MANO_V) continue;
-            um |= mask[v];
-            for (int cdim = 0; cdim < 3; ++cdim) tab[6 * (i >> 1) + 2 * cdim + (i & 1)] = v_template[v * 3 + cdim];
+        for (int i = 0; i < MF_VPT; ++i) {
+            const int v = g * MF_VPT + i;
+            if (v < MANO_V) um |= mask[v];
         }
-        for (int q = 0; q < 5; ++q) if (tip_ids[q] / MF_GV == g) tabi[25] |= 1 << q;
+        for (int q = 0; q < 5; ++q) if (tip_ids[q] / MF_VPT == g) tabi[1] |= 1 << q;
         int nu = 0;
         for (int j = 0; j < 16; ++j)
             if (um & (1u << j)) {
-                tabi[32 + nu] = 12 * j;
-                for (int i = 0; i < MF_GV; ++i) {
-                    const int v = g * MF_GV + i;
+                if (nu == MF_MAX_UNION) { union_fits = false; break; }
+                tabi[4 + nu] = 12 * j;
+                for (int i = 0; i < MF_VPT; ++i) {
+                    const int v = g * MF_VPT + i;
                     if (v >= MANO_V || lbs_weights[v * 16 + j] == 0.f) continue;
-                    tab[64 + nu * MF_GV + i] = lbs_weights[v * 16 + j];
-                    tabi[32 + nu] |= 1 << (16 + (i >> 1));
+                    tab[4 + MF_MAX_UNION + nu * MF_VPT + i] = lbs_weights[v * 16 + j];
+                    tabi[4 + nu] |= 1 << (16 + (i >> 1));
                 }
                 ++nu;
             }
-        tabi[24] = nu;
+        tabi[0] = nu;
     }
     {   // output slots: joint_map[k] = source (0..15 chain joint, 16..20 fingertip)
         int count[21] = {0};
@@ -945,8 +956,17 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
             ++count[src];
             if (src < 16) c->mano.chain_slot[src] = k; else c->mano.tip_slot[src - 16] = k;
         }
-        c->mano_fused_ok = true;
+        c->mano_fused_ok = union_fits;
         for (int q = 0; q < 21; ++q) if (count[q] != 1) c->mano_fused_ok = false;   // not a permutation: 3-kernel path
+        for (int j = 0; j < 16; ++j) if (parents[j] != mf_parent(j)) c->mano_fused_ok = false;   // prologue is specialised for the MANO tree
+        for (int j = 0; j < 16; ++j) {
+            c->mano_chain.chain_slot[j] = c->mano.chain_slot[j];
+            for (int cdim = 0; cdim < 3; ++cdim) {
+                c->mano_chain.jreg[j][cdim][0] = jt[j * 3 + cdim];
+                for (int l = 0; l < 10; ++l) c->mano_chain.jreg[j][cdim][1 + l] = js[(j * 3 + cdim) * 10 + l];
+            }
+        }
+        for (int q = 0; q < 5; ++q) { c->mano_chain.tip_slot[q] = c->mano.tip_slot[q]; c->mano_chain.tip_ids[q] = tip_ids[q]; }
     }
     for (void* p : c->mano_allocs) cudaFree(p);
     c->mano_allocs.clear();
@@ -982,11 +1002,6 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         if (!make_tmap_bf16_2d(&c->tm_mcoef, c->m_coef, ch, MANO_KTOT, MANO_KTOT, GEMM_BM) ||
             !make_tmap_bf16_2d(&c->tm_mbasis, c->mano.basis16, MANO_NPAD, MANO_KTOT, MANO_KTOT, 128 / c->plan.cta_group))
             return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed");
-        const size_t fc = MANO_FCHUNK;
-        HM_CUDA(c, cudaMalloc(&d, fc * MANO_KB * 2)); c->mano_allocs.push_back(d); c->mf_coef = reinterpret_cast<__half*>(d);
-        HM_CUDA(c, cudaMemset(c->mf_coef, 0, fc * MANO_KB * 2));
-        HM_CUDA(c, cudaMalloc(&d, fc * MANO_J * 48)); c->mano_allocs.push_back(d); c->mf_Au = reinterpret_cast<float*>(d);
-        HM_CUDA(c, cudaMemset(c->mf_Au, 0, fc * MANO_J * 48));
         if (!make_tmap_bf16_2d(&c->tm_fbasis, c->mano.basis16f, MANO_NPAD, MANO_KB, MANO_KB, MF_BN / 2))
             return fail(c, HM_ERR_CUDA, "hm_set_mano: tensor-map encoding failed (fused)");
     }
@@ -1003,15 +1018,10 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
     return HM_OK;
 }
 
-int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride,
-                  int frame_on_device, const double* boxes_xyxy, const uint8_t* is_right, int n,
-                  float* img_out, float* box_center, float* box_size, float* trans, void* stream) {
-    if (!c) return HM_ERR_INVALID;
-    if (!frame_bgr || !boxes_xyxy || !is_right || !img_out || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3)
-        return fail(c, HM_ERR_INVALID, "hm_preprocess: bad arguments");
-    if (n <= 0) return fail(c, HM_ERR_INVALID, "Invalid detections format");   // infer.py:360-361
-    if (n > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_preprocess: n exceeds max_batch");
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+// Common body of hm_preprocess / hm_preprocess_centers: ccs = [n][cx, cy, size] of the square source windows (for mode 2
+// cx is given in the mirrored image), mode 0 = plain, 1 = mirror the patch after the warp, 2 = sample the mirrored image.
+static int preprocess_impl(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
+                           const double* ccs, const uint8_t* mode, int n, float* img_out, float* trans, cudaStream_t s) {
     HM_CUDA(c, cudaSetDevice(c->device));
     if (c->crop_event_pending) {   // pinned staging still owned by the previous call's copy?
         HM_CUDA(c, cudaEventSynchronize(c->crop_event));
@@ -1022,19 +1032,21 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
     if (c->crop_kernel_recorded) HM_CUDA(c, cudaStreamWaitEvent(s, c->crop_kernel_event, 0));
     double band_lo = (double)H, band_hi = -1.0;   // source rows any crop can read (host frames: only these are uploaded)
     for (int i = 0; i < n; ++i) {
-        const double* box = boxes_xyxy + 4 * i;
-        if (!(box[2] > box[0]) || !(box[3] > box[1])) return fail(c, HM_ERR_INVALID, "hm_preprocess: empty box");
-        double cx, cy, size, M[6];
-        box_to_affine(box, &cx, &cy, &size, M);
+        const double cx = ccs[3 * i], cy = ccs[3 * i + 1], size = ccs[3 * i + 2];
+        if (!(size > 0)) return fail(c, HM_ERR_INVALID, "hm_preprocess: empty box");
+        if (mode[i] > 2) return fail(c, HM_ERR_INVALID, "hm_preprocess: bad crop mode");
+        double M[6];
+        center_to_affine(cx, cy, size, M);
         if (cy - 0.5 * size < band_lo) band_lo = cy - 0.5 * size;
         if (cy + 0.5 * size > band_hi) band_hi = cy + 0.5 * size;
-        c->crop_win[i][0] = cx - 0.5 * size; c->crop_win[i][1] = cx + 0.5 * size;
+        // columns of the ORIGINAL frame the crop reads (mode 2 samples column W - 1 - x)
+        const double xa = cx - 0.5 * size, xb = cx + 0.5 * size;
+        c->crop_win[i][0] = mode[i] == 2 ? (double)(W - 1) - xb : xa;
+        c->crop_win[i][1] = mode[i] == 2 ? (double)(W - 1) - xa : xb;
         c->crop_win[i][2] = cy - 0.5 * size; c->crop_win[i][3] = cy + 0.5 * size;
         invert_affine(M, c->crop_host[i].m);
-        c->crop_host[i].flip = is_right[i] ? 0 : 1;
+        c->crop_host[i].flip = mode[i];
         c->crop_host[i].pad = 0;
-        if (box_center) { box_center[2 * i] = (float)cx; box_center[2 * i + 1] = (float)cy; }
-        if (box_size) box_size[i] = (float)size;
         if (trans) for (int q = 0; q < 6; ++q) trans[6 * i + q] = (float)M[q];
     }
     const uint8_t* frame = frame_bgr;
@@ -1083,6 +1095,38 @@ int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row
     HM_CUDA(c, cudaEventRecord(c->crop_kernel_event, s));
     c->crop_kernel_recorded = true;
     return HM_OK;
+}
+
+int hm_preprocess(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride,
+                  int frame_on_device, const double* boxes_xyxy, const uint8_t* is_right, int n,
+                  float* img_out, float* box_center, float* box_size, float* trans, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!frame_bgr || !boxes_xyxy || !is_right || !img_out || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3)
+        return fail(c, HM_ERR_INVALID, "hm_preprocess: bad arguments");
+    if (n <= 0) return fail(c, HM_ERR_INVALID, "Invalid detections format");   // infer.py:360-361
+    if (n > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_preprocess: n exceeds max_batch");
+    std::vector<double> ccs((size_t)n * 3);
+    std::vector<uint8_t> mode((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const double* box = boxes_xyxy + 4 * i;
+        if (!(box[2] > box[0]) || !(box[3] > box[1])) return fail(c, HM_ERR_INVALID, "hm_preprocess: empty box");
+        box_to_center_size(box, &ccs[3 * i], &ccs[3 * i + 1], &ccs[3 * i + 2]);
+        mode[i] = is_right[i] ? 0 : 1;                                          // left hands: cv2.flip(patch, 1) (infer.py:229-230)
+        if (box_center) { box_center[2 * i] = (float)ccs[3 * i]; box_center[2 * i + 1] = (float)ccs[3 * i + 1]; }
+        if (box_size) box_size[i] = (float)ccs[3 * i + 2];
+    }
+    return preprocess_impl(c, frame_bgr, H, W, row_stride, frame_on_device, ccs.data(), mode.data(), n, img_out, trans,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hm_preprocess_centers(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
+                          const double* center_size, const uint8_t* mode, int n, float* img_out, float* trans, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!frame_bgr || !center_size || !mode || !img_out || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3)
+        return fail(c, HM_ERR_INVALID, "hm_preprocess_centers: bad arguments");
+    if (n <= 0 || n > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_preprocess_centers: n out of range");
+    return preprocess_impl(c, frame_bgr, H, W, row_stride, frame_on_device, center_size, mode, n, img_out, trans,
+                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hm_profile_enable(hm_ctx* c, int on) {
@@ -1199,10 +1243,63 @@ int hm_forward(hm_ctx* c, const float* img, int B, const hm_outputs* out, void* 
                     out->pred_keypoints_2d, s);
 }
 
+// ---- multi-GPU: one context per rank / GPU, crops sharded by the caller, one all-gather of the per-hand records --------
+#define HM_NCCL(ctx, call)                                                                                    \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess)                                                                                \
+            return fail(ctx, HM_ERR_CUDA, std::string(#call) + ": " + nccl_api().GetErrorString(r_));         \
+    } while (0)
+
+int hm_comm_unique_id(uint8_t* id_out) {
+    if (!id_out) return fail(nullptr, HM_ERR_INVALID, "hm_comm_unique_id: null pointer");
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(nullptr, HM_ERR_UNSUPPORTED, api.error);
+    static_assert(sizeof(ncclUniqueId) == HM_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, HM_ERR_CUDA, std::string("ncclGetUniqueId: ") + api.GetErrorString(r));
+    memcpy(id_out, &id, sizeof(id));
+    return HM_OK;
+}
+
+int hm_comm_init(hm_ctx* c, const uint8_t* id, int nranks, int rank) {
+    if (!c) return HM_ERR_INVALID;
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, HM_ERR_INVALID, "hm_comm_init: bad arguments");
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(c, HM_ERR_UNSUPPORTED, api.error);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    if (c->comm) { api.CommDestroy(c->comm); c->comm = nullptr; }
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    HM_NCCL(c, api.CommInitRank(&c->comm, nranks, uid, rank));
+    c->comm_ranks = nranks;
+    return HM_OK;
+}
+
+int hm_comm_destroy(hm_ctx* c) {
+    if (!c) return HM_ERR_INVALID;
+    if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; c->comm_ranks = 0; }
+    return HM_OK;
+}
+
+int hm_allgather(hm_ctx* c, void* nccl_comm, const float* local_records, float* global_records, int B_local, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!local_records || !global_records || B_local <= 0) return fail(c, HM_ERR_INVALID, "hm_allgather: bad arguments");
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(c, HM_ERR_UNSUPPORTED, api.error);
+    ncclComm_t comm = nccl_comm ? reinterpret_cast<ncclComm_t>(nccl_comm) : c->comm;
+    if (!comm) return fail(c, HM_ERR_STATE, "hm_allgather: no communicator (hm_comm_init, or pass an ncclComm_t)");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    HM_NCCL(c, api.AllGather(local_records, global_records, (size_t)B_local * HM_RECORD_FLOATS, ncclFloat, comm,
+                             reinterpret_cast<cudaStream_t>(stream)));
+    return HM_OK;
+}
+
 int hm_forward_launch_count(const hm_ctx* ctx) {
     // im2col + patch GEMM + 32 x (LN, qkv, attention, proj, LN, fc1, fc2) + last LN
-    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO (prep, fused blend + skinning)
-    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + ((ctx && (ctx->mano_legacy || !ctx->mano_fused_ok)) ? 3 : 2);
+    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO (one fused kernel; 3 on the three-kernel path)
+    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + ((ctx && (ctx->mano_legacy || !ctx->mano_fused_ok)) ? 3 : 1);
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------
@@ -1222,6 +1319,28 @@ int hm_test_gemm(hm_ctx* c, int cta_group, int bn, int epi, int w_format, const 
     p.b_format = w_format ? 1u : 0u;
     GemmPlan plan{cta_group == 1 ? 1 : 2, bn};
     HM_CUDA(c, gemm_launch(plan, epi, ta, tb, tout, p, c->num_sms, reinterpret_cast<cudaStream_t>(stream)));
+    return HM_OK;
+}
+
+// diagnostics: run hm_mano_lbs once with the fused kernel's phase clocks enabled and copy them to `clocks_out`
+// (HOST [n_ctas * 8 * 6] int64; n_ctas = 148).  Layout per CTA and unit (first 8 units): unit start, previous unit done on
+// all warps, inputs landed, prologue done, MMA may start, tiles done.
+int hm_test_mano_clocks(hm_ctx* c, const float* betas, const float* rotmats, int B, float* verts, float* joints21,
+                        long long* clocks_out, int n_ctas, void* stream) {
+    int rc = check_ready(c, B, false, true);
+    if (rc) return rc;
+    if (!clocks_out || n_ctas <= 0) return fail(c, HM_ERR_INVALID, "hm_test_mano_clocks: bad arguments");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n_ctas * 8 * 6 * sizeof(long long);
+    HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->mano_clk), bytes));
+    cudaMemset(c->mano_clk, 0, bytes);
+    rc = lbs_impl(c, betas, rotmats, nullptr, B, verts, joints21, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(clocks_out, c->mano_clk, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(c->mano_clk);
+    c->mano_clk = nullptr;
+    if (rc) return rc;
+    HM_CUDA(c, e);
     return HM_OK;
 }
 

@@ -49,8 +49,8 @@ struct ManoDevice {
     const int32_t* warp_nu;    // [25] size of each warp's joint union
     const int32_t* warp_union; // [25][16] joint ids
     const float* lane_w;       // [800][16] skinning weight of the thread's vertex for each union slot
-    // fused kernel (mano_fused.cuh): per 16-vertex group, the union of joints and the weights per union slot
-    const float4* fz_tab;      // [50][96 float4]: template | joint ids | union size | weights [16 slots][16 vertices]
+    // fused kernel (mano_fused.cuh): per vertex group, the union of joints, pair masks and weights per union slot
+    const float4* fz_tab;      // [MF_LIVE_GROUPS][MF_TAB_STRIDE / 16]
     int32_t parents[16];
     int32_t tip_ids[5];
     int32_t joint_map[21];
@@ -66,16 +66,9 @@ struct ManoPrepArgs {
     float* A;              // [B,16,12] skinning transforms (3x4 row-major)
     float* jpos;           // [B,16,3] posed joints
     int B;
-    // FUSED layout: coef [B,160] (no duplication), A as [hand/128][joint][hand%128][12], chain joints
-    // written straight to their output slots (+ projection)
-    float* joints;         // [B,21,3]
-    float* kp2d;           // [B,21,2] or null
-    const float* cam_t;    // [B,3] or null
-    float focal_over_size;
 };
 
 // 16 lanes per hand (lane = joint), 8 hands per 128-thread block.
-template <bool FUSED>
 __global__ void __launch_bounds__(128)
 mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
     ptx::pdl_prologue();
@@ -88,7 +81,7 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
     const float* be = a.betas + (size_t)(live ? h : 0) * 10;
     // ---- blend coefficients (fp16, duplicated for the hi / lo halves of the basis): 10 per lane ----
     if (live) {
-        __half* co = a.coef + (size_t)h * (FUSED ? MANO_KB : MANO_KTOT);
+        __half* co = a.coef + (size_t)h * MANO_KTOT;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const int k = j * 10 + i * 2;
@@ -98,7 +91,6 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
                 const int kk = k + q;
                 float c = 0.f;
                 if (kk < 10) c = be[kk];
-                else if (FUSED && kk >= 145 && kk < 155) c = be[kk - 145];   // betas again, for the "shape lo" basis columns
                 else if (kk < 145) {
                     // kk - 10 = (joint-1)*9 + row*3 + col; the diagonal entries ((kk - 10) % 9 in {0,4,8}) come from a
                     // 160-bit constant mask instead of an integer modulo per element
@@ -109,7 +101,7 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
             }
             const __half2 p = __floats2half2_rn(v[0], v[1]);
             *reinterpret_cast<__half2*>(co + k) = p;
-            if (!FUSED) *reinterpret_cast<__half2*>(co + MANO_KB + k) = p;
+            *reinterpret_cast<__half2*>(co + MANO_KB + k) = p;
         }
     }
     // ---- rest joint of this lane ------------------------------------------------------------------
@@ -156,8 +148,7 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
     }
     if (!live) return;
     // ---- outputs: A = G with translation t - R_glob J_rest; posed joint = translation of G --------
-    float* Ao = FUSED ? a.A + (((size_t)(h >> 7) * MANO_J + j) * 128 + (h & 127)) * 12
-                      : a.A + ((size_t)h * MANO_J + j) * 12;
+    float* Ao = a.A + ((size_t)h * MANO_J + j) * 12;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         float4 v;
@@ -165,23 +156,8 @@ mano_prep_kernel(const ManoDevice m, const ManoPrepArgs a) {
         v.w = G[r * 4 + 3] - (G[r * 4 + 0] * Jj[0] + G[r * 4 + 1] * Jj[1] + G[r * 4 + 2] * Jj[2]);
         reinterpret_cast<float4*>(Ao)[r] = v;
     }
-    if constexpr (!FUSED) {
-        float* jo = a.jpos + ((size_t)h * MANO_J + j) * 3;
-        jo[0] = G[3]; jo[1] = G[7]; jo[2] = G[11];
-    } else {
-        const int k = m.chain_slot[j];
-        if (k >= 0) {
-            float* jo = a.joints + ((size_t)h * 21 + k) * 3;
-            jo[0] = G[3]; jo[1] = G[7]; jo[2] = G[11];
-            if (a.kp2d != nullptr) {
-                const float* t = a.cam_t + (size_t)h * 3;
-                const float X = G[3] + t[0], Y = G[7] + t[1], Z = G[11] + t[2];
-                float* ko = a.kp2d + ((size_t)h * 21 + k) * 2;
-                ko[0] = a.focal_over_size * (X / Z);
-                ko[1] = a.focal_over_size * (Y / Z);
-            }
-        }
-    }
+    float* jo = a.jpos + ((size_t)h * MANO_J + j) * 3;
+    jo[0] = G[3]; jo[1] = G[7]; jo[2] = G[11];
 }
 
 struct ManoSkinArgs {

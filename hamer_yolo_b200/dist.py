@@ -8,6 +8,8 @@ packed record per hand over NCCL / NVLink.
 Record layout (float32, RECORD_FLOATS = 2599 values = 10,396 bytes per hand):
   verts 778*3 | kp3d 21*3 | kp2d 21*2 | cam 3 | cam_t 3 | rotmats 16*9 | betas 10
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -54,10 +56,34 @@ def unpack_outputs(rec):
     }
 
 
-def all_gather_records(rec_local, counts, group=None):
+def init_comm(engine, group=None):
+    """Give ``engine`` (one hm_ctx = one rank = one GPU) its own NCCL communicator through the C ABI: rank 0 creates the
+    id (hm_comm_unique_id), torch.distributed only ferries the 128 bytes, every rank joins with hm_comm_init.  After this,
+    all_gather_records(..., engine=engine) is ncclAllGather issued by libhamer_b200.so (hm_allgather)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ident = [None]
+    if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        rc = engine.lib.hm_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f'hm_comm_unique_id failed ({rc}): {engine.lib.hm_last_error(None).decode()}')
+        ident = [bytes(buf)]
+    dist.broadcast_object_list(ident, src=0, group=group)
+    raw = (C.c_uint8 * 128).from_buffer_copy(ident[0])
+    with torch.cuda.device(engine.device):
+        engine.check(engine.lib.hm_comm_init(engine.h, raw, world, rank))
+    engine.comm_ranks = world
+    return engine
+
+
+def all_gather_records(rec_local, counts, group=None, engine=None):
     """Gather every rank's [B_r, RECORD_FLOATS] block into [sum(B_r), RECORD_FLOATS] on all ranks.
-    Equal counts use one all_gather_into_tensor (ncclAllGather); ragged counts pad to the max."""
-    world = dist.get_world_size(group)
+    Equal counts are one ncclAllGather; ragged counts pad to the max.  With ``engine`` (after init_comm) the collective
+    is issued by the library itself (hm_allgather) on the current stream, otherwise by torch.distributed."""
+    world = getattr(engine, 'comm_ranks', 0) if engine is not None else 0
+    if not world:
+        engine = None
+        world = dist.get_world_size(group)
     assert len(counts) == world
     bmax = max(counts)
     if rec_local.shape[0] != bmax:
@@ -65,7 +91,14 @@ def all_gather_records(rec_local, counts, group=None):
                           device=rec_local.device)
         rec_local = torch.cat([rec_local, pad], dim=0)
     out = torch.empty(world * bmax, rec_local.shape[1], dtype=rec_local.dtype, device=rec_local.device)
-    dist.all_gather_into_tensor(out, rec_local.contiguous(), group=group)
+    if engine is not None:
+        rec_local = rec_local.contiguous()
+        assert rec_local.is_cuda and rec_local.dtype == torch.float32 and rec_local.shape[1] == RECORD_FLOATS
+        with torch.cuda.device(engine.device):
+            engine.check(engine.lib.hm_allgather(engine.h, None, C.c_void_p(rec_local.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 bmax, engine.stream()))
+    else:
+        dist.all_gather_into_tensor(out, rec_local.contiguous(), group=group)
     if all(c == bmax for c in counts):
         return out
     return torch.cat([out[r * bmax:r * bmax + counts[r]] for r in range(world)], dim=0)
@@ -86,5 +119,5 @@ def forward_sharded(model, img_all, group=None):
         # fewer hands than ranks (2 hands of a video frame on 8 GPUs): this rank has nothing to run but must still take
         # part in the collective, with a zero-row record (all_gather_records pads it to the largest shard)
         rec_local = torch.zeros(0, RECORD_FLOATS, dtype=torch.float32, device=img_all.device)
-    rec = all_gather_records(rec_local, counts, group)
+    rec = all_gather_records(rec_local, counts, group, engine=getattr(model, 'engine', None))
     return unpack_outputs(rec)

@@ -61,6 +61,7 @@ class Engine:
         self.use_graphs = bool(use_graphs)
         self._graphs = {}
         self._profiling = False
+        self.comm_ranks = 0        # > 0 once dist.init_comm gave this context its own NCCL communicator
 
     def close(self):
         self._graphs = {}
@@ -241,6 +242,32 @@ class Engine:
                 C.c_void_p(size.ctypes.data), C.c_void_p(trans.ctypes.data), self.stream()))
         return img, center, size, trans
 
+    def preprocess_centers(self, frame_bgr, center_size, modes, out=None):
+        """Crop windows given directly: center_size [n,3] float64 (c_x, c_y, size), modes [n] uint8 (0 plain, 1 mirror the
+        patch, 2 warp the mirrored frame - include/hamer_b200.h hm_preprocess_centers).  Returns (img, trans)."""
+        ccs = np.ascontiguousarray(center_size, dtype=np.float64).reshape(-1, 3)
+        n = ccs.shape[0]
+        md = np.ascontiguousarray(modes, dtype=np.uint8).reshape(-1)
+        img = out if out is not None else torch.empty(n, 3, IMG, IMG, device=self.device, dtype=torch.float32)
+        trans = np.empty((n, 2, 3), np.float32)
+        if isinstance(frame_bgr, torch.Tensor):
+            assert frame_bgr.is_cuda and frame_bgr.dtype == torch.uint8 and frame_bgr.stride(-1) == 1
+            H, W = frame_bgr.shape[:2]
+            fptr, stride, on_dev, keep = frame_bgr.data_ptr(), frame_bgr.stride(0), 1, frame_bgr
+        else:
+            keep = np.ascontiguousarray(frame_bgr)
+            assert keep.dtype == np.uint8 and keep.ndim == 3 and keep.shape[2] == 3
+            H, W = keep.shape[:2]
+            fptr, stride, on_dev = keep.ctypes.data, keep.strides[0], 0
+        with torch.cuda.device(self.device):
+            for lo in range(0, n, self.max_batch):
+                hi = min(n, lo + self.max_batch)
+                self.check(self.lib.hm_preprocess_centers(
+                    self.h, C.c_void_p(fptr), H, W, stride, on_dev, C.c_void_p(ccs[lo:hi].ctypes.data),
+                    C.c_void_p(md[lo:hi].ctypes.data), hi - lo, _ptr(img[lo:hi]), C.c_void_p(trans[lo:hi].ctypes.data),
+                    self.stream()))
+        return img, trans
+
     def camera_postprocess(self, pred_cam, kp3d, meta, fxfy_differ, add_center):
         """meta: CUDA float32 [n, >=16] (layout: include/hamer_b200.h).  kp3d is flipped in place.
         Returns (cam_t_full [n,3], kp2d_full [n,21,2])."""
@@ -342,6 +369,23 @@ class HAMER:
         }
         pred_mano_params['trans'] = t['pred_cam_t']                                     # hamer.py:155
         return output, pred_mano_params
+
+    def forward(self, batch):
+        return self.forward_step(batch, train=False)
+
+    __call__ = forward
+
+
+class HAMER_INFER(HAMER):
+    """The reference's inference-only module (hamer/hamer/models/hamer.py:468-563): ``forward(batch)`` returns ONE dict -
+    the ``output`` of HAMER.forward_step plus 'pose' (B,16,3,3) = cat(global_orient, hand_pose) and 'beta' (B,10)
+    (hamer.py:536-541) - and no second pred_mano_params dict."""
+
+    def forward_step(self, batch, train=False):
+        output, params = super().forward_step(batch, train=train)
+        output['pose'] = torch.cat([params['global_orient'], params['hand_pose']], dim=1)      # hamer.py:538-540
+        output['beta'] = params['betas']                                                      # hamer.py:541
+        return output
 
     def forward(self, batch):
         return self.forward_step(batch, train=False)

@@ -108,6 +108,16 @@ int hm_preprocess(hm_ctx* ctx, const uint8_t* frame_bgr, int H, int W, int64_t r
                   int frame_on_device, const double* boxes_xyxy, const uint8_t* is_right, int n,
                   float* img_out, float* box_center, float* box_size, float* trans, void* stream);
 
+/* hm_preprocess_centers: the same crop / warp / normalise kernel for callers that derive the crop windows themselves
+ * - ViTDetDataset.__getitem__ (hamer/hamer/datasets/vitdet_dataset.py:48-95) computes centre and size in float32 and
+ * flips INSIDE the warp (generate_image_patch_cv2 do_flip, hamer/hamer/datasets/utils.py:347-349).
+ *   center_size: HOST [n,3] float64 (c_x, c_y, bbox_size) of the square source window; mode: HOST [n]
+ *   0 = plain crop, 1 = mirror the patch after the warp (infer.py:229-230), 2 = warp the horizontally mirrored frame
+ *   (c_x is then the centre in the mirrored frame, W - c_x - 1).  trans: HOST [n,2,3] f32 or NULL. */
+int hm_preprocess_centers(hm_ctx* ctx, const uint8_t* frame_bgr, int H, int W, int64_t row_stride,
+                          int frame_on_device, const double* center_size, const uint8_t* mode, int n,
+                          float* img_out, float* trans, void* stream);
+
 /* hm_forward replaces HAMER.forward(batch) (hamer/hamer/models/hamer.py:269-277 -> forward_step
  * :99-156): img = batch['img'], DEVICE [B,3,256,256] float32. */
 int hm_forward(hm_ctx* ctx, const float* img, int B, const hm_outputs* out, void* stream);
@@ -136,6 +146,26 @@ int hm_mano_lbs(hm_ctx* ctx, const float* betas, const float* rotmats, const flo
 int hm_camera_postprocess(hm_ctx* ctx, const float* pred_cam, float* kp3d, const float* meta, int meta_stride,
                           int fxfy_differ, int add_center, int n, float* cam_t_full, float* kp2d_full, void* stream);
 
+/* ---- multi-GPU --------------------------------------------------------------------------------
+ * The reference runs one process and one hand at a time (hamer/infer.py:1268-1274); crops are independent, so the path
+ * shards data-parallel: one context per rank / GPU, each rank runs hm_forward on its crops, and ONE collective gathers the
+ * per-hand records (north_star).  A record is HM_RECORD_FLOATS float32 values per hand:
+ *   verts 778*3 | kp3d 21*3 | kp2d 21*2 | pred_cam 3 | pred_cam_t 3 | rotmats 16*9 (global_orient, hand_pose) | betas 10
+ * = 2599 floats = 10,396 bytes (hamer_yolo_b200/dist.py packs / unpacks it).
+ *   hm_comm_unique_id : rank 0 creates the 128-byte NCCL id and hands it to the other ranks by any out-of-band channel
+ *   hm_comm_init      : every rank joins (ncclCommInitRank on the context's device); the context owns the communicator
+ *   hm_allgather      : ncclAllGather of B_local records per rank into global_records [nranks * B_local][2599] on
+ *                       `stream` (no host synchronisation; equal counts on every rank - callers pad ragged shards).
+ *                       nccl_comm: an existing ncclComm_t to use instead of the context's own, or NULL.
+ * NCCL is resolved at run time (libnccl.so.2 already loaded in the process, else the system library). */
+#define HM_COMM_ID_BYTES 128
+#define HM_RECORD_FLOATS 2599
+int hm_comm_unique_id(uint8_t* id_out /* HOST [HM_COMM_ID_BYTES] */);
+int hm_comm_init(hm_ctx* ctx, const uint8_t* id, int nranks, int rank);
+int hm_comm_destroy(hm_ctx* ctx);
+int hm_allgather(hm_ctx* ctx, void* nccl_comm, const float* local_records, float* global_records, int B_local,
+                 void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels hm_forward(B) launches (for bench.py's gpu_launches). */
 int hm_forward_launch_count(const hm_ctx* ctx);
@@ -158,6 +188,9 @@ int hm_profile_collect(hm_ctx* ctx, double* ms_per_cat, int32_t* spans_per_cat, 
 int hm_test_gemm(hm_ctx* ctx, int cta_group, int bn, int epi, int w_format, const uint16_t* A,
                  const uint16_t* W, const float* bias, const float* pos, void* out, int M, int N,
                  int K, void* stream);
+/* hm_mano_lbs once with the fused kernel's per-unit phase clocks recorded (diagnostics; clocks_out HOST [n_ctas*8*6] int64) */
+int hm_test_mano_clocks(hm_ctx* ctx, const float* betas, const float* rotmats, int B, float* verts, float* joints21,
+                        long long* clocks_out, int n_ctas, void* stream);
 /* y = LayerNorm(x) over rows of 1280 (out_f16 != 0: fp16 output, else f32) */
 int hm_test_layernorm(hm_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y,
                       int rows, float eps, int out_f16, void* stream);

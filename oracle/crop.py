@@ -168,3 +168,35 @@ def prepare_batch_bbox(img_bgr, boxes):
     return {'img': np.stack(imgs), 'box_center': np.stack(cen), 'box_size': np.stack(siz),
             'img_size': np.stack(isz), 'inv_trans': np.stack(tr), 'trans': np.stack(tr),
             'do_flip': np.stack(flips)}
+
+
+def vitdet_item(img_bgr, box, right, rescale_factor=2.5):
+    """ViTDetDataset.__getitem__ (hamer/hamer/datasets/vitdet_dataset.py:48-95) for boxes that need no anti-alias blur:
+    float32 box arithmetic (:37-42, 52-58), flip INSIDE the warp (generate_image_patch_cv2 do_flip,
+    datasets/utils.py:347-349: the frame is mirrored and c_x = img_width - c_x - 1), BGR->RGB, CHW float32, normalise.
+    Returns (img (3,256,256) f32, box_center (2,) f32, box_size f32)."""
+    b = np.asarray(box, dtype=np.float32)
+    center = (b[2:4] + b[0:2]) / 2.0
+    scale = rescale_factor * (b[2:4] - b[0:2]) / 200.0
+    wh = scale * 200
+    w, h = wh
+    w_t, h_t = BBOX_SHAPE
+    if h / w < h_t / w_t:
+        new = np.array([w, max(w * h_t / w_t, h)])
+    else:
+        new = np.array([max(h * w_t / h_t, w), h])
+    bbox_size = new.max()
+    assert (bbox_size * 1.0) / IMAGE_SIZE / 2.0 <= 1.1, 'anti-aliased item: not restated'
+    c_x, c_y = center[0], center[1]
+    img = img_bgr
+    if right == 0:
+        img = img[:, ::-1, :]
+        c_x = img.shape[1] - c_x - 1
+    M = affine_from_box(float(c_x), float(c_y), float(bbox_size))
+    patch = warp_affine_u8(np.ascontiguousarray(img), M)[:, :, ::-1]
+    t = np.transpose(patch, (2, 0, 1)).astype(np.float32)
+    mean = 255.0 * np.array(IMAGE_MEAN)
+    std = 255.0 * np.array(IMAGE_STD)
+    for c in range(3):     # float32 arithmetic (numpy 1.x value-based casting of the float64 scalars, as in infer.py:235-238)
+        t[c] = (t[c] - np.float32(mean[c])) / np.float32(std[c])
+    return t, center, bbox_size

@@ -27,3 +27,20 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print(f'mano_lbs {nh} hands: {ms:.4f} ms  {nh * 10204 / ms / 1e6:.1f} GB/s')
+if os.environ.get('HM_MANO_CLOCKS'):
+    import ctypes as C
+    import numpy as np
+    n_ctas = 148
+    clk = np.zeros((n_ctas, 8, 6), np.int64)
+    eng.check(eng.lib.hm_test_mano_clocks(eng.h, C.c_void_p(betas.data_ptr()), C.c_void_p(rot.data_ptr()), nh, C.c_void_p(v.data_ptr()),
+                                          C.c_void_p(j.data_ptr()), C.c_void_p(clk.ctypes.data), n_ctas, eng.stream()))
+    d = np.diff(clk, axis=2).astype(np.float64)
+    names = ['wait prev unit (bar)', 'wait inputs', 'prologue', 'joint flush + bar', 'tiles']
+    live = clk[:, :, 5] > 0
+    for u in range(8):
+        m = live[:, u]
+        if m.sum() == 0:
+            continue
+        print(f'unit {u} ({int(m.sum())} CTAs): ' + ', '.join(f'{names[k]} {np.median(d[m, u, k]):.0f}' for k in range(5)))
+    tot = clk[:, :, 5].max(axis=1) - clk[:, 0, 0]
+    print('per-CTA first-unit-start to last-unit-end: median', np.median(tot), 'max', tot.max())

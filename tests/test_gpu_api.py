@@ -186,3 +186,55 @@ def test_opt_in_programmatic_dependent_launch(tmp_path):
         subprocess.run([sys.executable, str(script), str(out)], check=True, env=env, timeout=240)
         outs.append(torch.load(out))
     assert torch.equal(outs[0], outs[1])
+
+
+def test_vitdet_dataset_and_hamer_infer(model, oracle_model):
+    """ViTDetDataset mirror (vitdet_dataset.py:16-95: float32 box arithmetic, flip inside the warp) is bit-exact against
+    the oracle, and HAMER_INFER returns the single dict of hamer.py:536-553."""
+    from hamer_yolo_b200 import ViTDetDataset, HAMER_INFER
+    from hamer_yolo_b200.configs import default_config
+    from oracle import crop as oc
+    frame = synthetic_frame(480, 640, 31)
+    boxes = np.array([[100, 80, 260, 280], [330.5, 120.25, 490, 330], [-20, 30, 120, 200]], np.float32)   # crop windows < 563 px
+    right = np.array([1, 0, 0])
+    ds = ViTDetDataset(default_config(), frame, boxes, right, engine=model.engine)
+    assert len(ds) == 3
+    b = ds.batch()
+    for i in range(3):
+        t, center, size = oc.vitdet_item(frame, boxes[i], right[i])
+        item = ds[i]
+        assert np.array_equal(item['img'], t) and np.array_equal(b['img'][i].cpu().numpy(), t)
+        assert np.array_equal(item['box_center'], center) and item['box_size'] == size and item['right'] == right[i]
+        assert item['personid'] == i and np.array_equal(item['img_size'], np.array([640., 480.]))
+    with pytest.raises(NotImplementedError):
+        ViTDetDataset(default_config(), frame, np.array([[0, 0, 600, 400]], np.float32), np.array([1]), engine=model.engine)[0]
+    infer = HAMER_INFER.__new__(HAMER_INFER)
+    infer.__dict__.update(model.__dict__)                    # same engine / weights, the inference-only surface
+    out = infer({'img': b['img'][:2]})
+    ref, ref_params = model({'img': b['img'][:2]})
+    assert isinstance(out, dict) and set(out) == set(ref) | {'pose', 'beta'}
+    assert out['pose'].shape == (2, 16, 3, 3) and out['beta'].shape == (2, 10)
+    assert torch.allclose(out['pose'][:, :1], out['pred_mano_params']['global_orient'])
+
+
+def test_allgather_entry_point_single_rank(model):
+    """hm_comm_unique_id / hm_comm_init / hm_allgather through the C ABI with a one-rank communicator (what a 1-GPU box
+    can run): the gather is the identity.  The N-rank case runs in tests/test_gpu_multi.py on boxes with >= 2 GPUs."""
+    import ctypes as C
+    from hamer_yolo_b200 import dist as hd
+    eng = model.engine
+    buf = (C.c_uint8 * 128)()
+    assert eng.lib.hm_comm_unique_id(buf) == 0
+    eng.check(eng.lib.hm_comm_init(eng.h, buf, 1, 0))
+    eng.comm_ranks = 1
+    try:
+        rec = torch.randn(5, hd.RECORD_FLOATS, device=eng.device)
+        out = hd.all_gather_records(rec, [5], engine=eng)
+        torch.cuda.synchronize()
+        assert torch.equal(out, rec)
+    finally:
+        eng.check(eng.lib.hm_comm_destroy(eng.h))
+        eng.comm_ranks = 0
+    from hamer_yolo_b200._lib import HmError
+    with pytest.raises(HmError):
+        eng.check(eng.lib.hm_allgather(eng.h, None, C.c_void_p(rec.data_ptr()), C.c_void_p(out.data_ptr()), 5, eng.stream()))

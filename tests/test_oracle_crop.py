@@ -103,3 +103,33 @@ def test_example_images_config1():
             ref, _ = reference_patch(img, tuple(float(v) for v in box))
             cx, cy, size = oc.box_to_center_size(*[float(v) for v in box])
             assert np.array_equal(oc.warp_affine_u8(img, oc.affine_from_box(cx, cy, size)), ref)
+
+
+def test_vitdet_item_against_reference_functions():
+    """oracle.crop.vitdet_item (ViTDetDataset.__getitem__, vitdet_dataset.py:48-95) against the reference's own
+    expand_to_aspect_ratio / gen_trans_from_patch_cv recipe executed with cv2 (flip inside the warp: the frame is
+    mirrored and c_x = W - c_x - 1, datasets/utils.py:347-349)."""
+    frame = synthetic_frame(300, 400, 5)
+    for box, right in [((50, 60, 180, 220), 1), ((200.5, 40.25, 330, 250), 0), ((-30, 10, 90, 140), 0)]:
+        t, center, size = oc.vitdet_item(frame, box, right)
+        b = np.asarray(box, np.float32)
+        c = (b[2:4] + b[0:2]) / 2.0
+        sc = 2.5 * (b[2:4] - b[0:2]) / 200.0
+        bs = oc.expand_to_aspect_ratio(sc * 200).max()          # float64 restatement: same value for these boxes
+        assert np.float32(bs) == np.float32(size) and np.array_equal(c, center)
+        img, cx = frame, c[0]
+        if right == 0:
+            img = np.ascontiguousarray(frame[:, ::-1, :])
+            cx = frame.shape[1] - cx - 1
+        src = np.zeros((3, 2), np.float32)
+        src[0] = [cx, c[1]]
+        src[1] = src[0] + np.array([0, np.float32(size) * 0.5], np.float32)
+        src[2] = src[0] + np.array([np.float32(size) * 0.5, 0], np.float32)
+        dst = np.array([[128, 128], [128, 256], [256, 128]], np.float32)
+        M = cv2.getAffineTransform(src, dst)
+        patch = cv2.warpAffine(img, M, (256, 256), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        ref = np.transpose(patch[:, :, ::-1], (2, 0, 1)).astype(np.float32)
+        mean = 255. * np.array([0.485, 0.456, 0.406]); std = 255. * np.array([0.229, 0.224, 0.225])
+        for ch in range(3):
+            ref[ch] = (ref[ch] - np.float32(mean[ch])) / np.float32(std[ch])
+        assert np.array_equal(t, ref)
