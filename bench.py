@@ -109,6 +109,77 @@ def time_oracle_cpu(sample_crops, iters, warmup=1):
     return sample_crops / dt, dt, cores
 
 
+def gpu_eager_baseline(dev, sd, batch, iters=3):
+    """The "cuBLAS via PyTorch" bar: the reference's PyTorch path (oracle restatement,
+    same weights) run by torch eager on this B200 - fp32 (TF32 off, the reference default) and fp16 autocast."""
+    import torch
+    from oracle.pipeline import OHamer
+    from hamer_yolo_b200.mano_data import synthetic_mano
+    model = OHamer(synthetic_mano(0))
+    model.load_state_dict({k: v.to('cpu') for k, v in sd.items()})
+    model = model.to(dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    img = torch.randn(batch, 3, 256, 256, generator=g, device=dev)
+    out = {}
+    for name, ctx in (('fp32', None), ('fp16_autocast', torch.autocast('cuda', dtype=torch.float16))):
+        def once():
+            if ctx is None:
+                return model({'img': img})
+            with ctx:
+                return model({'img': img})
+        for _ in range(2):
+            once()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            o, _ = once()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {'value': batch / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms}
+    out['batch'] = batch
+    out['what'] = 'oracle restatement of the reference PyTorch path, torch eager on this GPU (cuBLAS / ATen kernels), device-resident inputs'
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def config0_pass(model, sd):
+    """BASELINE configs[0] shape of work (infer.py on example images: one image at a time, 1-2 boxes, batch = hands of the
+    image) on five synthetic 480x640 frames with fixed boxes (the example JPEGs do not travel to the GPU box): ms per
+    image through hamer_inference.estimate_from_rgb, checked against the CPU oracle on the same crops."""
+    import numpy as np
+    import torch
+    from bench_video import synthetic_frame
+    from hamer_yolo_b200 import hamer_inference
+    from oracle import crop as oc
+    from oracle.pipeline import OHamer
+    from hamer_yolo_b200.mano_data import synthetic_mano
+    hi = hamer_inference(model=model)
+    ora = OHamer(synthetic_mano(0))
+    ora.load_state_dict({k: v.to('cpu') for k, v in sd.items()})
+    cases = [[['right', [100, 80, 260, 300]], ['left', [330, 120, 520, 420]]], [['left', [40, 60, 300, 400]]],
+             [['right', [300, 200, 420, 330]], ['right', [60, 50, 180, 220]]], [['left', [200, 100, 460, 440]]],
+             [['right', [380, 260, 600, 470]]]]
+    frames = [synthetic_frame(480, 640, 40 + i) for i in range(5)]
+    for f, d in zip(frames, cases):                                   # warm-up (graphs per batch size)
+        hi.estimate_from_rgb(f, d)
+    torch.cuda.synchronize()
+    lat, err = [], 0.0
+    for f, d in zip(frames, cases):
+        t0 = time.perf_counter()
+        out, _ = hi.estimate_from_rgb(f, d)
+        v = out['pred_vertices'].cpu()
+        lat.append((time.perf_counter() - t0) * 1e3)
+        batch = {k: torch.from_numpy(x) for k, x in oc.prepare_batch_bbox(f, d).items()}
+        ref, _ = ora(batch)
+        err = max(err, (v - ref['pred_vertices']).norm(dim=-1).max().item() * 1e3)
+    return {'images': 5, 'hands': sum(len(d) for d in cases), 'ms_per_image': float(np.mean(lat)),
+            'max_vertex_error_mm_vs_cpu_oracle': err,
+            'what': 'BASELINE configs[0] shape: one image at a time, batch = hands of the image, host frame in / vertices out'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -157,10 +228,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     B = args.batch
-    model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0),
-                          device=dev, max_batch=B)
+    if args.scaling == 'strong':                   # BASELINE configs[2]: 512 crops in total, sharded over the ranks
+        B = max(1, args.global_batch // world)
+    sd = random_state_dict(seed=0, device=dev)
+    model, _ = load_hamer(state_dict=sd, mano=synthetic_mano(0), device=dev, max_batch=B)
     eng = model.engine
     eng.use_graphs = not args.no_graphs
+    collective = 'none'
+    if world > 1:
+        try:                                       # the library's own communicator: hm_allgather = ncclAllGather from the C ABI
+            hd.init_comm(eng)
+            collective = 'hm_allgather (ncclAllGather issued by libhamer_b200.so)'
+        except Exception as exc:                   # noqa: BLE001
+            collective = f'torch.distributed all_gather_into_tensor (hm_comm_init failed: {exc})'[:200]
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     img = torch.randn(B, 3, 256, 256, generator=g, device=dev)
     img_host = img.cpu().pin_memory()
@@ -170,7 +250,7 @@ def run_ours(args):
         out, _ = model({'img': x})
         rec = hd.pack_outputs(out)
         if world > 1:
-            rec = hd.all_gather_records(rec, counts)
+            rec = hd.all_gather_records(rec, counts, engine=eng)
         return rec
 
     def sync_all():
@@ -312,19 +392,34 @@ def run_ours(args):
                          f'path, torch CPU with {cores} threads, {dt:.2f} s per iteration'}
 
     launches = eng.launch_count() + 3 + (1 if world > 1 else 0)       # + input copy, result clone, packing (+ all-gather)
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get('gemm_family_mean_mb_per_launch')
+        tj = json.load(open(tp))
+        traffic = tj.get('per_kernel')                # MB per launch per GEMM family, all from one build (tag in `source`)
+        traffic_src = tj.get('source')
+
+    # ---- other configurations of BASELINE.json, reported as extra keys (N = 1 only) -----------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        try:
+            extras['gpu_eager_baseline'] = gpu_eager_baseline(dev, sd, 16)
+        except Exception as exc:                   # noqa: BLE001
+            extras['gpu_eager_baseline'] = {'error': str(exc)[:200]}
+        import bench_video
+        v = bench_video.run(model, args.video_frames, 10)
+        extras['video'] = {k: v[k] for k in ('p50_ms', 'p99_ms', 'mean_ms', 'frames', 'mean_hands_per_frame', 'hands_per_s')}
+        extras['video']['what'] = 'BASELINE configs[4]: 1920x1080 host frames, 2-8 hands per frame, estimate_from_rgb, per-frame sync'
+        extras['config0'] = config0_pass(model, sd)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic',
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic',
         'config': {'workload': f'HaMeR ViT-H/16 (32 blocks, 192 tokens) + MANO decoder head + MANO LBS, synthetic '
                                f'256x192 crops, batch {B} per GPU, random-init weights (BASELINE config[1]'
                                + (f'; {world * B} crops sharded over {world} GPUs + all-gather of MANO outputs' if world > 1 else '') + ')',
                    'batch_per_gpu': B, 'global_batch': world * B,
-                   'parallelism': f'dp{world}' if world > 1 else 'single',
+                   'parallelism': f'dp{world}' if world > 1 else 'single', 'collective': collective,
                    'dtype_detail': 'fp16 tensor-core operands (tcgen05 kind::f16, same rate as bf16), fp32 '
                                    'accumulate / residual / LayerNorm / softmax; decoder head and MANO in fp32',
                    'launch': 'CUDA graph of hm_forward per batch size (Engine.use_graphs); roofline pass un-graphed with per-launch events',
@@ -335,7 +430,8 @@ def run_ours(args):
                 'd2h_bytes_per_step': int(host_rec.numel() * 4)},
         'gpu_launches': launches * args.steps,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
-                     'frac': achieved / peaks['tf_sustained'], 'traffic': traffic, 'traffic_unit': 'MB per launch (ncu dram read+write, profiles/ncu_traffic.json)',
+                     'frac': achieved / peaks['tf_sustained'], 'traffic': traffic, 'traffic_unit': 'MB per launch per GEMM family (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+                     'traffic_source': traffic_src,
                      'kernel': 'gemm_bf16_tn_kernel (tcgen05/TMA GEMM, all epilogues; 129 launches per step)',
                      'peak_source': f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                      'per_family_tflops': per_family,
@@ -349,6 +445,7 @@ def run_ours(args):
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -363,6 +460,11 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches (for ncu launch lists)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --batch crops per GPU (default); strong: --global-batch crops in total (BASELINE configs[2])')
+    ap.add_argument('--global-batch', type=int, default=512)
+    ap.add_argument('--no-extras', action='store_true', help='skip the gpu_eager_baseline / video / config0 keys')
+    ap.add_argument('--video-frames', type=int, default=200)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -25,21 +25,17 @@ def synthetic_frame(h, w, seed):
     return np.clip(base + rng.integers(-40, 40, (h, w, 3)), 0, 255).astype(np.uint8)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--frames', type=int, default=500)
-    ap.add_argument('--warmup', type=int, default=20)
-    args = ap.parse_args()
-    from hamer_yolo_b200 import load_hamer, hamer_inference, synthetic_mano
-    from hamer_yolo_b200.weights import random_state_dict
-    dev = torch.device('cuda', 0)
-    model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0),
-                          device=dev, max_batch=8)
+def run(model, n_frames=500, warmup=20):
+    """The video loop on an already loaded model; returns the result dict (bench.py embeds it as its `video` key)."""
+    from hamer_yolo_b200 import hamer_inference
+    args = argparse.Namespace(frames=n_frames, warmup=warmup)
     hi = hamer_inference(model=model)
     frames = [synthetic_frame(1080, 1920, s) for s in range(8)]
     rng = np.random.default_rng(0)
     k_real = np.array([[1400., 0, 960.], [0, 1400., 540.], [0, 0, 1]], np.float32)
     lat, hands = [], []
+    for n in range(2, 9):                           # every hand count once before timing (first use captures its CUDA graph)
+        hi.estimate_from_rgb(frames[0], [['right', [100.0 * n, 100.0, 100.0 * n + 150, 300.0]]] * n, k_real)
     for i in range(args.warmup + args.frames):
         n = int(rng.integers(2, 9))
         dets = []
@@ -64,7 +60,20 @@ def main():
             'hands_per_s': float(np.sum(hands) / (lat.sum() / 1e3)), 'higher_is_better': False,
             'data': 'synthetic', 'config': {'workload': 'BASELINE config[4] video stream', 'n_gpus': 1,
                                             'api': 'hamer_inference.estimate_from_rgb (host frame, per-frame sync)'}}
-    print(json.dumps(line))
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--frames', type=int, default=500)
+    ap.add_argument('--warmup', type=int, default=20)
+    args = ap.parse_args()
+    from hamer_yolo_b200 import load_hamer, synthetic_mano
+    from hamer_yolo_b200.weights import random_state_dict
+    dev = torch.device('cuda', 0)
+    model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0),
+                          device=dev, max_batch=8)
+    print(json.dumps(run(model, args.frames, args.warmup)))
 
 
 if __name__ == '__main__':

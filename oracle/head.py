@@ -142,7 +142,7 @@ class OManoHead(nn.Module):
 
     def forward(self, feats):
         B = feats.shape[0]
-        token = torch.zeros(B, 1, 1, dtype=feats.dtype)
+        token = torch.zeros(B, 1, 1, dtype=feats.dtype, device=feats.device)
         token_out = self.transformer(token, feats).squeeze(1)
         pose6d = self.decpose(token_out) + self.init_hand_pose
         betas = self.decshape(token_out) + self.init_betas

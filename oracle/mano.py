@@ -31,12 +31,12 @@ def _t(a, dtype=torch.float32):
 def lbs(betas, rot_mats, mano):
     """smplx.lbs.lbs with pose2rot=False.  betas (B,10), rot_mats (B,16,3,3) ->
     vertices (B,778,3), posed joints (B,16,3)."""
-    dtype = betas.dtype
-    v_template = _t(mano['v_template'], dtype)
-    shapedirs = _t(mano['shapedirs'], dtype)
-    posedirs = _t(mano['posedirs'], dtype)
-    J_regressor = _t(mano['J_regressor'], dtype)
-    lbs_weights = _t(mano['lbs_weights'], dtype)
+    dtype, dev = betas.dtype, betas.device
+    v_template = _t(mano['v_template'], dtype).to(dev)
+    shapedirs = _t(mano['shapedirs'], dtype).to(dev)
+    posedirs = _t(mano['posedirs'], dtype).to(dev)
+    J_regressor = _t(mano['J_regressor'], dtype).to(dev)
+    lbs_weights = _t(mano['lbs_weights'], dtype).to(dev)
     parents = [int(p) for p in mano.get('parents', PARENTS)]
     B = betas.shape[0]
     nj = J_regressor.shape[0]
@@ -46,7 +46,7 @@ def lbs(betas, rot_mats, mano):
     # vertices2joints: einsum('bik,ji->bjk')
     J = torch.einsum('bik,ji->bjk', v_shaped, J_regressor)
     # pose blend shapes from (R - I) of the non-root joints
-    ident = torch.eye(3, dtype=dtype)
+    ident = torch.eye(3, dtype=dtype, device=dev)
     pose_feature = (rot_mats[:, 1:] - ident).reshape(B, -1)
     v_posed = v_shaped + torch.matmul(pose_feature, posedirs).view(B, -1, 3)
 
@@ -54,7 +54,7 @@ def lbs(betas, rot_mats, mano):
     joints = J.unsqueeze(-1)
     rel = joints.clone()
     rel[:, 1:] = rel[:, 1:] - joints[:, parents[1:]]
-    tm = torch.zeros(B, nj, 4, 4, dtype=dtype)
+    tm = torch.zeros(B, nj, 4, 4, dtype=dtype, device=dev)
     tm[:, :, :3, :3] = rot_mats
     tm[:, :, :3, 3:] = rel
     tm[:, :, 3, 3] = 1.0
@@ -63,14 +63,14 @@ def lbs(betas, rot_mats, mano):
         chain.append(torch.matmul(chain[parents[i]], tm[:, i]))
     transforms = torch.stack(chain, dim=1)
     posed_joints = transforms[:, :, :3, 3]
-    jh = torch.cat([joints, torch.zeros(B, nj, 1, 1, dtype=dtype)], dim=2)
+    jh = torch.cat([joints, torch.zeros(B, nj, 1, 1, dtype=dtype, device=dev)], dim=2)
     shift = torch.matmul(transforms, jh)                     # (B,nj,4,1)
     A = transforms.clone()
     A[:, :, :, 3:] = A[:, :, :, 3:] - shift                  # rel_transforms
 
     # skinning
     T = torch.matmul(lbs_weights[None].expand(B, -1, -1), A.view(B, nj, 16)).view(B, -1, 4, 4)
-    vh = torch.cat([v_posed, torch.ones(B, v_posed.shape[1], 1, dtype=dtype)], dim=2)
+    vh = torch.cat([v_posed, torch.ones(B, v_posed.shape[1], 1, dtype=dtype, device=dev)], dim=2)
     verts = torch.matmul(T, vh.unsqueeze(-1))[:, :, :3, 0]
     return verts, posed_joints
 

@@ -43,7 +43,7 @@ class OHamer(nn.Module):
         params, pred_cam = self.mano_head(feats)                         # :121
         out = {'pred_cam': pred_cam,
                'pred_mano_params': {k: v.clone() for k, v in params.items()}}
-        focal = FOCAL_LENGTH * torch.ones(B, 2, dtype=x.dtype)
+        focal = FOCAL_LENGTH * torch.ones(B, 2, dtype=x.dtype, device=x.device)
         cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2],
                              2 * focal[:, 0] / (IMAGE_SIZE * pred_cam[:, 0] + 1e-9)], dim=-1)  # :131-134
         out['pred_cam_t'] = cam_t
