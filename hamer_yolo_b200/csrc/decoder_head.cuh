@@ -6,7 +6,7 @@
 // (utils/geometry.py:47-70) and pred_cam_t (hamer.py:131-134).
 //
 // The decoder has ONE query token per crop, so
-//   * self-attention: softmax over a single logit is 1  =>  SA(y) = to_out(W_v y)
+//   * self-attention: softmax over a single logit is 1  =>  SA(y) = to_out(W_v y) = (W_o W_v) y + b_o (merged at load time)
 //   * cross-attention: (W_k c_t) . q_h = c_t . (W_k,h^T q_h) and sum_t a_t W_v c_t = W_v sum_t a_t c_t
 //     => per layer 8 score vectors against the 192 context tokens and 8 pooled contexts replace the
 //     503 MFLOP K/V projection of the context (exact in real arithmetic).
@@ -20,11 +20,15 @@
 namespace hm {
 
 // ------------------------------------------------------------------------------------------------
-// Y[b, n] (+)= act( scale * sum_k X[b, k] * W[n, k] + bias[n] ),  b < B, n < N, K % 64 == 0, K <= 1280.
+// Y[b, n] = [R[b, n] +] act( scale * sum_k X'[b, k] * W[n, k] + bias[n] ),  b < B, n < N, K % 128 == 0, K <= 1280,
+// X' = X or LayerNorm(X) (PreNorm of the decoder, pose_transformer.py:27-40, eps 1e-5).
 // Batched over blockIdx.z with element strides (per-head products of the cross-attention).
-// Block = 8 warps = 8 output columns x a tile of 16 rows (crops): the whole [16 x K] X tile is staged
-// once in shared memory (cp.async), each warp keeps its W row in registers (K/32 floats per lane),
-// so there is one global round trip and one barrier per block; 64 KB of smem lets 3 blocks share an SM.
+// Block = 8 warps, tile = 16 rows (crops) x 8 CPW columns: the [16 x K] X tile is staged once in shared memory
+// (cp.async) and - with LNF - normalised there, two rows per warp.  A warp owns CPW output columns; their W rows are
+// copied by cp.async into lane-private shared-memory slots, all of them in flight from the first instruction on (the
+// block then only waits on its own copy groups, no barrier), so every X float4 read from shared memory feeds CPW x 4
+// FMAs: with CPW = 1 the kernel is bound by shared-memory reads (each warp re-reads the whole tile for one column);
+// CPW = 4 makes it FMA-bound.  The host picks the widest CPW that still gives every SM a block and fits 227 KB.
 // ------------------------------------------------------------------------------------------------
 enum SkinnyEpi : int { SK_NONE = 0, SK_GELU = 1, SK_RESID = 2 };
 
@@ -33,13 +37,20 @@ struct SkinnyParams {
     const float* W; long long w_bs;      // W row pitch = K
     const float* bias; int bias_bs;      // may be null
     float* Y; int ldy; long long y_bs;
+    const float* R; int ldr;             // SK_RESID: Y = R + (...); R == Y updates in place, R != Y is needed when X is R
+                                         // itself (PreNorm sub-layers: other blocks still read the rows this one updates)
     int B, N, K;
     float scale;                         // applied to the dot product before bias
+    const float *ln_g, *ln_b;            // LNF: LayerNorm weight / bias over the K inputs
+    float ln_eps;
 };
 
 constexpr int SK_ROWS = 16;     // crops per block tile
-constexpr int SK_COLS = 8;      // output columns (warps) per block
+constexpr int SK_WARPS = 8;
 constexpr int SK_KMAX = 1280;   // largest K (cross-attention value projection)
+constexpr int SK_SMEM_MAX = 200 * 1024;
+// X tile + the lane-private W slots (8 warps x CPW columns x K floats)
+__host__ __device__ constexpr size_t sk_smem_bytes(int K, int cpw) { return (size_t)(SK_ROWS + SK_WARPS * cpw) * K * sizeof(float); }
 
 __device__ __forceinline__ void sk_cp_async16(float* smem_dst, const float* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
@@ -62,153 +73,389 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(SK_COLS * 32)
+__device__ __forceinline__ void sk_cp_async_wait(int pending) {   // cp.async.wait_group takes an immediate
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    }
+}
+
+template <int CPW, int EPI, bool LNF>
+__global__ void __launch_bounds__(SK_WARPS * 32)
 skinny_linear_kernel(const SkinnyParams p) {
     ptx::pdl_prologue();
-    extern __shared__ __align__(16) float sk_xs[];              // [SK_ROWS][K]
+    extern __shared__ __align__(16) float sk_smem[];            // X tile [SK_ROWS][K], then the W slots
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * SK_COLS + warp;
+    const int n0 = (blockIdx.x * SK_WARPS + warp) * CPW;
     const int b0 = blockIdx.y * SK_ROWS;
     const int z = blockIdx.z;
     const float* X = p.X + z * p.x_bs;
     const float* W = p.W + z * p.w_bs;
     float* Y = p.Y + z * p.y_bs;
     const int rows = min(SK_ROWS, p.B - b0);
-    const bool active = n < p.N;
-    const int K = p.K, K4 = K >> 2;
+    const int K = p.K, K4 = K >> 2, KI = K >> 7, NG = (KI + 1) >> 1;   // W arrives in NG groups of two 128-wide K steps
+    float* sk_xs = sk_smem;
+    // this lane's private W slots: [step i][column c] float4 - written by its own cp.async, read back by itself, so the
+    // only synchronisation the W stream needs is cp.async.wait_group
+    float4* wslot = reinterpret_cast<float4*>(sk_smem + (size_t)SK_ROWS * K) + (size_t)warp * (KI * CPW * 32) + lane;
 
-    // X tile -> smem (rows >= rows are zero-filled so the inner loop has no predicates)
+    // Everything the block will read goes in flight at once (X tile 16 K floats, W 8 CPW K floats: up to 192 KB): the
+    // kernel is a latency chain otherwise (one block per SM, a handful of dependent round trips to L2 / HBM).
     for (int e = threadIdx.x; e < SK_ROWS * K4; e += blockDim.x) {
         const int r = e / K4, c = e - r * K4;
         float* dst = sk_xs + (size_t)r * K + c * 4;
         if (r < rows) sk_cp_async16(dst, X + (size_t)(b0 + r) * p.ldx + c * 4);
-        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // no predicates in the inner loop
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // this warp's W row: lane holds float4 chunks lane, lane + 32, ... (K / 128 of them, <= 10)
-    float4 w[SK_KMAX / 128];
+    const float* wrow[CPW];                                     // columns past N re-read the last valid row (results dropped)
 #pragma unroll
-    for (int i = 0; i < SK_KMAX / 128; ++i) {
-        const int c = lane + 32 * i;
-        w[i] = (active && c < K4) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K) + c)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < CPW; ++c) wrow[c] = W + (size_t)min(n0 + c, p.N - 1) * K + lane * 4;
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int i = 2 * g + ii;
+            if (i < KI) {
+#pragma unroll
+                for (int c = 0; c < CPW; ++c)
+                    sk_cp_async16(reinterpret_cast<float*>(wslot + (i * CPW + c) * 32), wrow[c] + i * 128);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    sk_cp_async_wait(NG);                                       // the X tile has landed
+    __syncthreads();
+    if constexpr (LNF) {
+        // PreNorm: rows 2 warp, 2 warp + 1 of the staged tile, two-pass statistics (same arithmetic as layernorm_kernel)
+        const float4* g4 = reinterpret_cast<const float4*>(p.ln_g);
+        const float4* b4 = reinterpret_cast<const float4*>(p.ln_b);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            float4* xr = reinterpret_cast<float4*>(sk_xs + (size_t)(2 * warp + rr) * K);
+            float4 v[SK_KMAX / 128];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < SK_KMAX / 128; ++i)
+                if (i < KI) { v[i] = xr[i * 32 + lane]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+            const float mean = warp_sum(s) / (float)K;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < SK_KMAX / 128; ++i)
+                if (i < KI) {
+                    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+                    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+                }
+            const float rstd = rsqrtf(warp_sum(q) / (float)K + p.ln_eps);
+#pragma unroll
+            for (int i = 0; i < SK_KMAX / 128; ++i)
+                if (i < KI) {
+                    const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+                    float4 o;
+                    o.x = v[i].x * rstd * g.x + b.x; o.y = v[i].y * rstd * g.y + b.y;
+                    o.z = v[i].z * rstd * g.z + b.z; o.w = v[i].w * rstd * g.w + b.w;
+                    xr[i * 32 + lane] = o;
+                }
+        }
+        __syncthreads();
+    }
+    float acc[CPW][SK_ROWS];
+#pragma unroll
+    for (int c = 0; c < CPW; ++c)
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r) acc[c][r] = 0.f;
+    const float4* xs4 = reinterpret_cast<const float4*>(sk_xs) + lane;
+    for (int g = 0; g < NG; ++g) {
+        sk_cp_async_wait(NG - 1 - g);                           // W group g has landed (groups complete in order)
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int i = 2 * g + ii;
+            if (i < KI) {
+                float4 wc[CPW];
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) wc[c] = wslot[(i * CPW + c) * 32];
+#pragma unroll
+                for (int r = 0; r < SK_ROWS; ++r) {
+                    const float4 x = xs4[(size_t)r * K4 + i * 32];
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c)
+                        acc[c][r] = fmaf(x.x, wc[c].x, fmaf(x.y, wc[c].y, fmaf(x.z, wc[c].z, fmaf(x.w, wc[c].w, acc[c][r]))));
+                }
+            }
+        }
+    }
+    const int r = lane & 15;
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+        float v = warp_transpose_reduce16(acc[c], lane);        // lanes i, i + 16: row i
+        const int n = n0 + c;
+        if (lane < 16 && r < rows && n < p.N) {
+            const float bias = p.bias ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
+            v = v * p.scale + bias;
+            if constexpr (EPI == SK_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+            if constexpr (EPI == SK_RESID) v += p.R[(size_t)(b0 + r) * p.ldr + n];
+            Y[(size_t)(b0 + r) * p.ldy + n] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention, step 1: u[b, h, c] = scale * sum_d W_k[h 64 + d, c] * q[b, h 64 + d]  (the key projection moved onto
+// the query, (W_k c_t) . q_h = c_t . (W_k,h^T q_h); W_k = to_kv.weight rows 0..511 in the checkpoint's own [512][1280] layout).
+// grid (1280 / 128, 8 heads, ceil(B / 16)), block 128: thread = context channel c (coalesced W reads), the 16 x 64 query
+// tile of the head sits in shared memory and is read as broadcasts; 64 independent weight loads per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+head_u_kernel(const float* __restrict__ q, const float* __restrict__ wk, float* __restrict__ u, int B, float scale) {
+    ptx::pdl_prologue();
+    __shared__ __align__(16) float qs[SK_ROWS][64];
+    const int h = blockIdx.y, b0 = blockIdx.z * SK_ROWS, rows = min(SK_ROWS, B - b0);
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const float* w = wk + (size_t)h * 64 * 1280 + c;
+    // all 64 weight loads of the thread go out before the query tile is staged: the barrier below keeps the FMAs (which
+    // need the tile) behind them, otherwise ptxas interleaves loads and FMAs eight at a time - eight exposed round trips
+    float wv[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(wv[d]) : "l"(w + (size_t)d * 1280));
+    for (int e = threadIdx.x; e < SK_ROWS * 16; e += 128) {
+        const int r = e >> 4, c4 = e & 15;
+        reinterpret_cast<float4*>(&qs[r][0])[c4] =
+            r < rows ? *reinterpret_cast<const float4*>(q + (size_t)(b0 + r) * 512 + h * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
     float acc[SK_ROWS];
 #pragma unroll
     for (int r = 0; r < SK_ROWS; ++r) acc[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < SK_KMAX / 128; ++i) {
-        const int c = lane + 32 * i;
-        if (i * 32 < K4) {                                      // block-uniform
-            const int cc = c < K4 ? c : 0;                      // lanes past a 64-wide tail re-read chunk 0 (w = 0)
+    for (int d4 = 0; d4 < 16; ++d4) {
 #pragma unroll
-            for (int r = 0; r < SK_ROWS; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(sk_xs + (size_t)r * K + cc * 4);
-                acc[r] = fmaf(x.x, w[i].x, fmaf(x.y, w[i].y, fmaf(x.z, w[i].z, fmaf(x.w, w[i].w, acc[r]))));
+        for (int r = 0; r < SK_ROWS; ++r) {
+            const float4 x = reinterpret_cast<const float4*>(&qs[r][0])[d4];
+            acc[r] = fmaf(x.x, wv[4 * d4], fmaf(x.y, wv[4 * d4 + 1], fmaf(x.z, wv[4 * d4 + 2], fmaf(x.w, wv[4 * d4 + 3], acc[r]))));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r)
+        if (r < rows) u[((size_t)(b0 + r) * 8 + h) * 1280 + c] = acc[r] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention, step 2, one pass over the context ("flash decoding" with a single query token per head):
+//   s[h, t] = feats[b, t, :] . u[b, h, :],  a = softmax_t(s),  pooled[b, h, :] = sum_t a[h, t] feats[b, t, :]
+// Persistent: one CTA per SM walks a contiguous range of work items, item = 16 context tokens of one crop (80 KB of
+// fp32 features = ONE contiguous run of the feature tensor).  The items stream through a two-deep shared-memory ring
+// by cp.async.bulk (the next item lands while this one is computed: the features leave HBM once per layer, nothing is
+// re-read through L2).  Per item:
+//   scores : warp = (8-token group, fifth of the 1280 channels): 8 tokens x 8 heads per lane, the u vectors from shared
+//            memory - every u float4 feeds 8 tokens, every x float4 8 heads (shared-memory reads balance the FMAs);
+//   softmax: running (max, sum) per head over the CTA's consecutive items of the same crop (online rescaling);
+//   pooling: thread j owns float4 column j of the 8 pooled vectors, accumulated in registers over the items.
+// When the crop (or the CTA's range) ends, the segment's un-normalised [8][1280] + (m, l) go to global memory; the
+// CTA whose segment completes the crop's 12 chunks (atomic ticket) merges the segments in chunk order.  The ranges
+// are a static function of (B, grid), so the summation order is fixed run to run; PER_CHUNK (hm_config.deterministic)
+// makes every item its own segment, which also makes it independent of the batch size.
+// ------------------------------------------------------------------------------------------------
+constexpr int XA_T = 16, XA_NCH = 192 / XA_T;
+constexpr int XA_THREADS = 320;
+constexpr uint32_t XA_CHUNK_BYTES = XA_T * 1280 * 4;
+constexpr uint32_t XA_OFF_U = 2 * XA_CHUNK_BYTES;                 // [8][1280] floats
+constexpr uint32_t XA_OFF_SC = XA_OFF_U + 8 * 1280 * 4;           // [5][16][8] partial scores
+constexpr uint32_t XA_OFF_PS = XA_OFF_SC + 5 * 16 * 8 * 4;        // [16][8] exp(s - m)
+constexpr uint32_t XA_OFF_WSM = XA_OFF_PS + 16 * 8 * 4;           // [12][8] merge weights
+constexpr uint32_t XA_OFF_RUN = XA_OFF_WSM + XA_NCH * 8 * 4;      // m_run[8], l_run[8], rescale[8]
+constexpr uint32_t XA_OFF_BAR = XA_OFF_RUN + 24 * 4;              // 2 mbarriers, then the is_last flag
+constexpr uint32_t XA_SMEM_BYTES = XA_OFF_BAR + 16 + 16;
+
+// first item of CTA c's range: items are split evenly and contiguously over the grid
+__device__ __forceinline__ int xa_range_start(int c, int items, int grid) { return (int)(((long long)c * items) / grid); }
+
+template <bool PER_CHUNK>
+__global__ void __launch_bounds__(XA_THREADS, 1)
+head_xattn_kernel(const float* __restrict__ feats, const float* __restrict__ u, float* __restrict__ part,
+                  float* __restrict__ ml, unsigned int* __restrict__ ticket, float* __restrict__ pooled, int B) {
+    extern __shared__ __align__(128) uint8_t xa_smem[];
+    float* us = reinterpret_cast<float*>(xa_smem + XA_OFF_U);
+    float* sc = reinterpret_cast<float*>(xa_smem + XA_OFF_SC);
+    float* ps = reinterpret_cast<float*>(xa_smem + XA_OFF_PS);
+    float* wsm = reinterpret_cast<float*>(xa_smem + XA_OFF_WSM);
+    float* mrun = reinterpret_cast<float*>(xa_smem + XA_OFF_RUN);
+    float* lrun = mrun + 8;
+    float* resc = mrun + 16;
+    uint64_t* full = reinterpret_cast<uint64_t*>(xa_smem + XA_OFF_BAR);
+    int* is_last = reinterpret_cast<int*>(xa_smem + XA_OFF_BAR + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int items = XA_NCH * B, G = gridDim.x;
+    const int i0 = xa_range_start(blockIdx.x, items, G), i1 = xa_range_start(blockIdx.x + 1, items, G);
+    ptx::griddep_launch_dependents();
+    if (tid == 0) {
+        ptx::mbar_init(&full[0], 1);
+        ptx::mbar_init(&full[1], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    ptx::griddep_wait();
+    auto issue = [&](int it, int buf) {          // one thread: the item's 80 KB as four bulk copies
+        const float* src = feats + (size_t)it * (XA_T * 1280);      // item it = tokens [16 it, 16 it + 16) of the flat [B 192] rows
+        ptx::mbar_arrive_expect_tx(&full[buf], XA_CHUNK_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            ptx::bulk_load_1d(xa_smem + buf * XA_CHUNK_BYTES + q * (XA_CHUNK_BYTES / 4), src + q * (XA_T / 4) * 1280,
+                              XA_CHUNK_BYTES / 4, &full[buf]);
+    };
+    if (tid == 0 && i0 < i1) issue(i0, 0);
+    int u_b = -1, seg_first = 0, seg_n = 0;
+    float4 acc[8];
+    for (int it = i0; it < i1; ++it) {
+        const int k = it - i0, buf = k & 1, b = it / XA_NCH, ch = it - b * XA_NCH;
+        if (tid == 0 && it + 1 < i1) issue(it + 1, buf ^ 1);       // the other slot was released by the barrier that ended item it - 1
+        if (b != u_b) {                                           // block-uniform: a new crop starts
+            const float4* ub = reinterpret_cast<const float4*>(u + (size_t)b * 8 * 1280);
+            for (int e = tid; e < 8 * 320; e += XA_THREADS) reinterpret_cast<float4*>(us)[e] = __ldg(ub + e);
+            u_b = b;
+            seg_n = 0;
+        }
+        if (seg_n == 0) {                                         // a new segment: reset the running softmax state
+            seg_first = ch;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < 8) { mrun[tid] = -INFINITY; lrun[tid] = 0.f; }
+        }
+        __syncthreads();
+        ptx::mbar_wait(&full[buf], (uint32_t)(k >> 1) & 1u);
+        const float4* xc = reinterpret_cast<const float4*>(xa_smem + buf * XA_CHUNK_BYTES);
+        {   // ---- scores: warp = (token group tg, channel fifth kf) ----
+            const int tg = warp / 5, kf = warp - tg * 5;
+            float a8[8][8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int h = 0; h < 8; ++h) a8[t][h] = 0.f;
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const int i = kf * 2 + ii;
+                float4 w[8];
+#pragma unroll
+                for (int h = 0; h < 8; ++h) w[h] = reinterpret_cast<const float4*>(us)[h * 320 + i * 32 + lane];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float4 x = xc[(tg * 8 + t) * 320 + i * 32 + lane];
+#pragma unroll
+                    for (int h = 0; h < 8; ++h)
+                        a8[t][h] = fmaf(x.x, w[h].x, fmaf(x.y, w[h].y, fmaf(x.z, w[h].z, fmaf(x.w, w[h].w, a8[t][h]))));
+                }
+            }
+#pragma unroll
+            for (int tp = 0; tp < 4; ++tp) {                      // two tokens x 8 heads = 16 values per reduction
+                float v16[16];
+#pragma unroll
+                for (int h = 0; h < 8; ++h) { v16[h] = a8[2 * tp][h]; v16[8 + h] = a8[2 * tp + 1][h]; }
+                const float r = warp_transpose_reduce16(v16, lane);   // lanes i, i + 16: value i
+                if (lane < 16) sc[(kf * 16 + tg * 8 + 2 * tp + (lane >> 3)) * 8 + (lane & 7)] = r;
             }
         }
-    }
-    float v = warp_transpose_reduce16(acc, lane);               // lanes i, i+16: row i
-    if (!active) return;
-    const int r = lane & 15;
-    if (lane < 16 && r < rows) {
-        const float bias = p.bias ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
-        v = v * p.scale + bias;
-        if constexpr (EPI == SK_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-        float* y = Y + (size_t)(b0 + r) * p.ldy + n;
-        if constexpr (EPI == SK_RESID) v += *y;
-        *y = v;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Cross-attention scores: sc[b, h, t] = sum_c feats[b, t, c] * u[b, h, c]   (u already carries the
-// 64^-0.5 scale).  grid (192/32, B), block 256: the 8 x 1280 u-vectors sit in smem, each warp owns
-// 4 context tokens.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-head_scores_kernel(const float* __restrict__ feats, const float* __restrict__ u,
-                   float* __restrict__ sc) {
-    ptx::pdl_prologue();
-    __shared__ __align__(16) float us[8][1280];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float4* ub = reinterpret_cast<const float4*>(u + (size_t)b * 8 * 1280);
-    for (int e = threadIdx.x; e < 8 * 320; e += 256) reinterpret_cast<float4*>(&us[0][0])[e] = ub[e];
-    __syncthreads();
-    // a warp owns 4 context tokens and walks them together: every u float4 read from shared memory
-    // feeds 4 tokens (the kernel was bound by shared-memory reads with one token at a time)
-    const int t0 = blockIdx.x * 32 + warp * 4;
-    const float4* f = reinterpret_cast<const float4*>(feats + ((size_t)b * 192 + t0) * 1280);
-    float acc[4][8];
+        __syncthreads();
+        if (warp < 8) {     // ---- warp = head: this item's weights against the running maximum ----
+            float v = -INFINITY;
+            if (lane < XA_T) {
+                v = 0.f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int h = 0; h < 8; ++h) acc[t][h] = 0.f;
-#pragma unroll 2
-    for (int i = 0; i < 10; ++i) {
-        float4 x[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) x[t] = f[(size_t)t * 320 + i * 32 + lane];
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            const float4 w = reinterpret_cast<const float4*>(&us[h][0])[i * 32 + lane];
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                acc[t][h] = fmaf(x[t].x, w.x, fmaf(x[t].y, w.y, fmaf(x[t].z, w.z, fmaf(x[t].w, w.w, acc[t][h]))));
+                for (int kf = 0; kf < 5; ++kf) v += sc[(kf * 16 + lane) * 8 + warp];
+            }
+            const float m_old = mrun[warp];
+            const float m_new = fmaxf(m_old, warp_max(v));
+            const float e = lane < XA_T ? expf(v - m_new) : 0.f;
+            const float l_item = warp_sum(e);
+            if (lane < XA_T) ps[lane * 8 + warp] = e;
+            if (lane == 0) {
+                const float so = expf(m_old - m_new);             // exp(-inf) = 0 on the first item of a segment
+                resc[warp] = so;
+                lrun[warp] = fmaf(lrun[warp], so, l_item);
+                mrun[warp] = m_new;
+            }
         }
-    }
+        __syncthreads();
+        {   // ---- pooling: thread = float4 column ----
+            const float4 r0 = *reinterpret_cast<const float4*>(resc), r1 = *reinterpret_cast<const float4*>(resc + 4);
+            const float so[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+            for (int h = 0; h < 8; ++h) { acc[h].x *= so[h]; acc[h].y *= so[h]; acc[h].z *= so[h]; acc[h].w *= so[h]; }
+#pragma unroll 4
+            for (int t = 0; t < XA_T; ++t) {
+                const float4 x = xc[t * 320 + tid];
+                const float4 a0 = *reinterpret_cast<const float4*>(ps + t * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(ps + t * 8 + 4);
+                const float w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            const float v = warp_sum(acc[t][h]);
-            if (lane == 0) sc[((size_t)b * 8 + h) * 192 + t0 + t] = v;
+                for (int h = 0; h < 8; ++h) {
+                    acc[h].x = fmaf(w[h], x.x, acc[h].x); acc[h].y = fmaf(w[h], x.y, acc[h].y);
+                    acc[h].z = fmaf(w[h], x.z, acc[h].z); acc[h].w = fmaf(w[h], x.w, acc[h].w);
+                }
+            }
         }
-}
-
-// ------------------------------------------------------------------------------------------------
-// softmax over the 192 tokens + attention-weighted pooling of the context:
-//   pooled[b, h, c] = sum_t softmax_t(sc[b, h, :])[t] * feats[b, t, c]
-// grid (1280/128, B), block 128: thread = context channel c (coalesced), 8 heads in registers.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-head_pool_kernel(const float* __restrict__ feats, const float* __restrict__ sc,
-                 float* __restrict__ pooled) {
-    ptx::pdl_prologue();
-    __shared__ __align__(16) float a[192][8];          // [token][head]: two float4 broadcasts per token
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int h = warp; h < 8; h += 4) {               // each warp normalises two heads
-        const float* s = sc + ((size_t)b * 8 + h) * 192;
-        float v[6], mx = -INFINITY;
+        ++seg_n;
+        const bool seg_end = PER_CHUNK || it + 1 == i1 || (it + 1) / XA_NCH != b;      // block-uniform
+        if (seg_end) {
+            const size_t slot = (size_t)b * XA_NCH + seg_first;
+            float4* dst = reinterpret_cast<float4*>(part + slot * 8 * 1280) + tid;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { v[i] = s[i * 32 + lane]; mx = fmaxf(mx, v[i]); }
-        mx = warp_max(mx);
-        float sum = 0.f;
+            for (int h = 0; h < 8; ++h) __stcg(dst + h * 320, acc[h]);
+            if (tid < 8) { ml[(slot * 8 + tid) * 2] = mrun[tid]; ml[(slot * 8 + tid) * 2 + 1] = lrun[tid]; }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) *is_last = (atomicAdd(ticket + b, (unsigned)seg_n) + (unsigned)seg_n == (unsigned)XA_NCH);
+            __syncthreads();
+            if (*is_last) {       // this segment completed the crop: merge the segments in chunk order
+                __threadfence();
+                if (tid < 8) {
+                    float M = -INFINITY, L = 0.f;
+#pragma unroll 1
+                    for (int s = 0; s < XA_NCH; ++s) {
+                        const int idx = b * XA_NCH + s;
+                        const int cta = (int)(((long long)idx * G + items - 1) / items);
+                        const bool start = PER_CHUNK || s == 0 || (cta < G && xa_range_start(cta, items, G) == idx);
+                        const float m = start ? __ldcg(ml + ((size_t)idx * 8 + tid) * 2) : -INFINITY;
+                        wsm[s * 8 + tid] = m;
+                        M = fmaxf(M, m);
+                    }
+#pragma unroll 1
+                    for (int s = 0; s < XA_NCH; ++s) {
+                        const float m = wsm[s * 8 + tid];
+                        const float e = m == -INFINITY ? 0.f : expf(m - M);
+                        if (e != 0.f) L = fmaf(e, __ldcg(ml + ((size_t)(b * XA_NCH + s) * 8 + tid) * 2 + 1), L);
+                        wsm[s * 8 + tid] = m == -INFINITY ? -1.f : e;          // -1 marks "no segment starts here"
+                    }
+                    const float inv = 1.0f / L;
+#pragma unroll 1
+                    for (int s = 0; s < XA_NCH; ++s) if (wsm[s * 8 + tid] >= 0.f) wsm[s * 8 + tid] *= inv;
+                }
+                if (tid == 0) ticket[b] = 0u;
+                __syncthreads();
+                const float4* src = reinterpret_cast<const float4*>(part + (size_t)b * XA_NCH * 8 * 1280) + tid;
+                float4 o[8];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
-        const float inv = 1.0f / warp_sum(sum);
+                for (int h = 0; h < 8; ++h) o[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int s = 0; s < XA_NCH; ++s) {
+                    if (wsm[s * 8] < 0.f) continue;                              // block-uniform
 #pragma unroll
-        for (int i = 0; i < 6; ++i) a[i * 32 + lane][h] = v[i] * inv;
+                    for (int h = 0; h < 8; ++h) {
+                        const float4 v = __ldcg(src + ((size_t)s * 8 + h) * 320);
+                        const float w = wsm[s * 8 + h];
+                        o[h].x = fmaf(w, v.x, o[h].x); o[h].y = fmaf(w, v.y, o[h].y);
+                        o[h].z = fmaf(w, v.z, o[h].z); o[h].w = fmaf(w, v.w, o[h].w);
+                    }
+                }
+                float4* dstp = reinterpret_cast<float4*>(pooled + (size_t)b * 8 * 1280) + tid;
+#pragma unroll
+                for (int h = 0; h < 8; ++h) dstp[h * 320] = o[h];
+            }
+            seg_n = 0;
+        }
+        __syncthreads();          // every thread is done with slot buf (and with sc / ps / wsm)
     }
-    __syncthreads();
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    const float* f = feats + (size_t)b * 192 * 1280 + c;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 8
-    for (int t = 0; t < 192; ++t) {
-        const float x = f[(size_t)t * 1280];
-        const float4 a0 = *reinterpret_cast<const float4*>(&a[t][0]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&a[t][4]);
-        acc[0] = fmaf(a0.x, x, acc[0]); acc[1] = fmaf(a0.y, x, acc[1]);
-        acc[2] = fmaf(a0.z, x, acc[2]); acc[3] = fmaf(a0.w, x, acc[3]);
-        acc[4] = fmaf(a1.x, x, acc[4]); acc[5] = fmaf(a1.y, x, acc[5]);
-        acc[6] = fmaf(a1.z, x, acc[6]); acc[7] = fmaf(a1.w, x, acc[7]);
-    }
-#pragma unroll
-    for (int h = 0; h < 8; ++h) pooled[((size_t)b * 8 + h) * 1280 + c] = acc[h];
 }
 
 // Broadcast the constant layer-0 token (to_token_embedding.bias + pos_embedding) to every crop.

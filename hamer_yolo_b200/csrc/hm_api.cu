@@ -21,6 +21,7 @@
 #include "decoder_head.cuh"
 #include "elementwise.cuh"
 #include "gemm_host.cuh"
+#include "letterbox.cuh"
 #include "mano_lbs.cuh"
 #include "mano_fused.cuh"
 
@@ -54,8 +55,8 @@ struct BlockW {
 };
 struct HeadLayerW {
     const float *n0g, *n0b, *n1g, *n1b, *n2g, *n2b;
-    const float *w_sa_v, *w_sa_o, *b_sa_o;            // to_qkv rows 1024.. (v), to_out
-    const float *w_q, *w_kT, *w_v, *w_ca_o, *b_ca_o;  // to_q, transposed k, to_kv rows 512.. (v), to_out
+    const float *w_sa, *b_sa_o;                       // single-token self-attention: to_out . W_v merged (1024 x 1024), to_out bias
+    const float *w_q, *w_k, *w_v, *w_ca_o, *b_ca_o;   // to_q, to_kv rows 0..511 (k) and 512.. (v), to_out
     const float *w1, *b1, *w2, *b2;                   // feed-forward
 };
 
@@ -102,7 +103,8 @@ struct hm_ctx {
     __nv_bfloat16* w_patch2 = nullptr;    // [1280, 1536] = [W | W]
     float* pos_tab = nullptr;             // [192, 1280] = pos[1:] + pos[0]
     float* tok0 = nullptr;                // [1024] layer-0 decoder token
-    float* w_kT[HDEPTH] = {};             // [8][1280][64] transposed key projections
+    unsigned int* hticket = nullptr;      // per-crop arrival counter of head_xattn_kernel (zero between launches)
+    float* w_sa[HDEPTH] = {};             // [1024][1024] = to_out.weight (1024 x 512) . to_qkv.weight[1024:1536] (512 x 1024)
     float* w_read = nullptr;              // [109, 1024]
     float* b_read = nullptr;              // [109] bias + init_*
     CUtensorMap tm_wpatch;
@@ -119,7 +121,7 @@ struct hm_ctx {
     CUtensorMap tm_x_out;   // fp32 residual stream as the target of the TMA reduce-add epilogue
     CUtensorMap tm_att128, tm_att32;   // qkv buffer: 64- and 16-column boxes for the attention kernel
     // decoder workspace
-    float *hx = nullptr, *hy = nullptr, *hv = nullptr, *hq = nullptr, *hu = nullptr, *hsc = nullptr,
+    float *hx = nullptr, *hx2 = nullptr, *hq = nullptr, *hu = nullptr, *hpart = nullptr, *hml = nullptr,
           *hpool = nullptr, *ho = nullptr, *hh = nullptr, *hraw = nullptr, *hrot = nullptr,
           *hcamt = nullptr, *hbetas = nullptr, *hscratch = nullptr;
 
@@ -323,19 +325,36 @@ void launch_ln(const float* x, const float* g, const float* b, OutT* y, int rows
     launch_pdl(layernorm_kernel<V, OutT>, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, y, rows, eps);
 }
 
-cudaError_t launch_skinny(int epi, const float* X, int ldx, long long x_bs, const float* W,
+template <int CPW, bool LNF>
+void launch_skinny_epi(int epi, dim3 grid, size_t smem, cudaStream_t s, const SkinnyParams& p) {
+    if (epi == SK_NONE) launch_pdl(skinny_linear_kernel<CPW, SK_NONE, LNF>, grid, dim3(SK_WARPS * 32), smem, s, p);
+    else if (epi == SK_GELU) launch_pdl(skinny_linear_kernel<CPW, SK_GELU, LNF>, grid, dim3(SK_WARPS * 32), smem, s, p);
+    else launch_pdl(skinny_linear_kernel<CPW, SK_RESID, LNF>, grid, dim3(SK_WARPS * 32), smem, s, p);
+}
+
+// ln_g != nullptr: the input rows are LayerNorm-ed (eps 1e-5, the decoder's PreNorm) inside the kernel
+cudaError_t launch_skinny(int num_sms, int epi, const float* X, int ldx, long long x_bs, const float* W,
                           long long w_bs, const float* bias, int bias_bs, float* Y, int ldy,
                           long long y_bs, int B, int N, int K, int batch, float scale,
-                          cudaStream_t s) {
+                          const float* ln_g, const float* ln_b, const float* resid, cudaStream_t s) {
     SkinnyParams p;
     p.X = X; p.ldx = ldx; p.x_bs = x_bs; p.W = W; p.w_bs = w_bs; p.bias = bias; p.bias_bs = bias_bs;
     p.Y = Y; p.ldy = ldy; p.y_bs = y_bs; p.B = B; p.N = N; p.K = K; p.scale = scale;
-    if (K % 64 != 0 || K > SK_KMAX || ldx % 4 != 0) return cudaErrorInvalidValue;
-    dim3 grid((N + SK_COLS - 1) / SK_COLS, (B + SK_ROWS - 1) / SK_ROWS, batch);
-    const size_t smem = (size_t)SK_ROWS * K * sizeof(float);
-    if (epi == SK_NONE) launch_pdl(skinny_linear_kernel<SK_NONE>, dim3(grid), dim3(SK_COLS * 32), smem, s, p);
-    else if (epi == SK_GELU) launch_pdl(skinny_linear_kernel<SK_GELU>, dim3(grid), dim3(SK_COLS * 32), smem, s, p);
-    else launch_pdl(skinny_linear_kernel<SK_RESID>, dim3(grid), dim3(SK_COLS * 32), smem, s, p);
+    p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = 1e-5f;
+    p.R = resid; p.ldr = ldy;
+    if (epi == SK_RESID && (!resid || batch != 1)) return cudaErrorInvalidValue;
+    if (K % 128 != 0 || K > SK_KMAX || ldx % 4 != 0) return cudaErrorInvalidValue;
+    // columns per warp: the widest tile that still gives (nearly) every SM a block
+    const int row_tiles = (B + SK_ROWS - 1) / SK_ROWS;
+    int cpw = 4;
+    while (cpw > 1 && (((N + SK_WARPS * cpw - 1) / (SK_WARPS * cpw)) * row_tiles * batch < (num_sms * 3) / 4 ||
+                       sk_smem_bytes(K, cpw) > SK_SMEM_MAX)) cpw >>= 1;
+    dim3 grid((N + SK_WARPS * cpw - 1) / (SK_WARPS * cpw), row_tiles, batch);
+    const size_t smem = sk_smem_bytes(K, cpw);
+    const bool lnf = ln_g != nullptr;
+    if (cpw == 4) { if (lnf) launch_skinny_epi<4, true>(epi, grid, smem, s, p); else launch_skinny_epi<4, false>(epi, grid, smem, s, p); }
+    else if (cpw == 2) { if (lnf) launch_skinny_epi<2, true>(epi, grid, smem, s, p); else launch_skinny_epi<2, false>(epi, grid, smem, s, p); }
+    else { if (lnf) launch_skinny_epi<1, true>(epi, grid, smem, s, p); else launch_skinny_epi<1, false>(epi, grid, smem, s, p); }
     return cudaGetLastError();
 }
 
@@ -388,31 +407,32 @@ int head_impl(hm_ctx* c, const float* feats, int B, const hm_outputs* out, cudaS
     ProfScope ps(c, s, PC_HEAD);
     launch_pdl(head_init_token_kernel, dim3((B * HD + 255) / 256), dim3(256), 0, s, c->tok0, c->hx, B);
     const float scale = 0.125f;   // dim_head ** -0.5 = 64^-0.5
+    const int nsm = c->num_sms;
+    const int row_tiles = (B + SK_ROWS - 1) / SK_ROWS;
+    float *xa = c->hx, *xb = c->hx2;   // token before / after the layer's self-attention (swapped per layer)
     for (int l = 0; l < HDEPTH; ++l) {
         const HeadLayerW& w = c->hl[l];
-        // self-attention on one token: x += to_out(W_v LN(x))
-        launch_ln<8, float>(c->hx, w.n0g, w.n0b, c->hy, B, 1e-5f, s);
-        HM_CUDA(c, launch_skinny(SK_NONE, c->hy, HD, 0, w.w_sa_v, 0, nullptr, 0, c->hv, 512, 0, B, 512, HD, 1, 1.f, s));
-        HM_CUDA(c, launch_skinny(SK_RESID, c->hv, 512, 0, w.w_sa_o, 0, w.b_sa_o, 0, c->hx, HD, 0, B, HD, 512, 1, 1.f, s));
-        // cross-attention against the 192 context tokens
-        launch_ln<8, float>(c->hx, w.n1g, w.n1b, c->hy, B, 1e-5f, s);
-        HM_CUDA(c, launch_skinny(SK_NONE, c->hy, HD, 0, w.w_q, 0, nullptr, 0, c->hq, 512, 0, B, 512, HD, 1, 1.f, s));
-        // u[b,h,:] = scale * W_k,h^T q[b,h,:]
-        HM_CUDA(c, launch_skinny(SK_NONE, c->hq, 512, 64, w.w_kT, (long long)DM * 64, nullptr, 0,
-                                 c->hu, 8 * DM, DM, B, DM, 64, 8, scale, s));
-        launch_pdl(head_scores_kernel, dim3(6, B), dim3(256), 0, s, feats, c->hu, c->hsc);
-        launch_pdl(head_pool_kernel, dim3(10, B), dim3(128), 0, s, feats, c->hsc, c->hpool);
+        // self-attention on one token: xb = xa + (W_o W_v) LN(xa) + b_o  (out of place: every block normalises whole rows of xa)
+        HM_CUDA(c, launch_skinny(nsm, SK_RESID, xa, HD, 0, w.w_sa, 0, w.b_sa_o, 0, xb, HD, 0, B, HD, HD, 1, 1.f, w.n0g, w.n0b, xa, s));
+        // cross-attention against the 192 context tokens: q = W_q LN(x), u[b,h,:] = scale * W_k,h^T q[b,h,:]
+        HM_CUDA(c, launch_skinny(nsm, SK_NONE, xb, HD, 0, w.w_q, 0, nullptr, 0, c->hq, 512, 0, B, 512, HD, 1, 1.f, w.n1g, w.n1b, nullptr, s));
+        launch_pdl(head_u_kernel, dim3(DM / 128, 8, row_tiles), dim3(128), 0, s, (const float*)c->hq, w.w_k, c->hu, B, scale);
+        {
+            const int xg = std::min(nsm, XA_NCH * B);
+            if (c->deterministic) launch_pdl(head_xattn_kernel<true>, dim3(xg), dim3(XA_THREADS), XA_SMEM_BYTES, s, feats, (const float*)c->hu, c->hpart, c->hml, c->hticket, c->hpool, B);
+            else launch_pdl(head_xattn_kernel<false>, dim3(xg), dim3(XA_THREADS), XA_SMEM_BYTES, s, feats, (const float*)c->hu, c->hpart, c->hml, c->hticket, c->hpool, B);
+        }
         // o[b, h*64 + d] = W_v,h pooled[b,h,:]
-        HM_CUDA(c, launch_skinny(SK_NONE, c->hpool, 8 * DM, DM, w.w_v, (long long)64 * DM, nullptr, 0,
-                                 c->ho, 512, 64, B, 64, DM, 8, 1.f, s));
-        HM_CUDA(c, launch_skinny(SK_RESID, c->ho, 512, 0, w.w_ca_o, 0, w.b_ca_o, 0, c->hx, HD, 0, B, HD, 512, 1, 1.f, s));
+        HM_CUDA(c, launch_skinny(nsm, SK_NONE, c->hpool, 8 * DM, DM, w.w_v, (long long)64 * DM, nullptr, 0,
+                                 c->ho, 512, 64, B, 64, DM, 8, 1.f, nullptr, nullptr, nullptr, s));
+        HM_CUDA(c, launch_skinny(nsm, SK_RESID, c->ho, 512, 0, w.w_ca_o, 0, w.b_ca_o, 0, xb, HD, 0, B, HD, 512, 1, 1.f, nullptr, nullptr, xb, s));
         // feed-forward
-        launch_ln<8, float>(c->hx, w.n2g, w.n2b, c->hy, B, 1e-5f, s);
-        HM_CUDA(c, launch_skinny(SK_GELU, c->hy, HD, 0, w.w1, 0, w.b1, 0, c->hh, HD, 0, B, HD, HD, 1, 1.f, s));
-        HM_CUDA(c, launch_skinny(SK_RESID, c->hh, HD, 0, w.w2, 0, w.b2, 0, c->hx, HD, 0, B, HD, HD, 1, 1.f, s));
+        HM_CUDA(c, launch_skinny(nsm, SK_GELU, xb, HD, 0, w.w1, 0, w.b1, 0, c->hh, HD, 0, B, HD, HD, 1, 1.f, w.n2g, w.n2b, nullptr, s));
+        HM_CUDA(c, launch_skinny(nsm, SK_RESID, c->hh, HD, 0, w.w2, 0, w.b2, 0, xb, HD, 0, B, HD, HD, 1, 1.f, nullptr, nullptr, xb, s));
+        std::swap(xa, xb);
     }
-    HM_CUDA(c, launch_skinny(SK_NONE, c->hx, HD, 0, c->w_read, 0, c->b_read, 0, c->hraw, NREAD, 0, B,
-                             NREAD, HD, 1, 1.f, s));
+    HM_CUDA(c, launch_skinny(nsm, SK_NONE, xa, HD, 0, c->w_read, 0, c->b_read, 0, c->hraw, NREAD, 0, B,
+                             NREAD, HD, 1, 1.f, nullptr, nullptr, nullptr, s));
     HeadOut ho;
     // outputs the caller skipped are routed into scratch so the kernel stays branch-free
     float* scratch = c->hscratch;
@@ -568,11 +588,16 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     CA(dev_alloc(c, &c->x, Mmax * DM));
     CA(dev_alloc(c, &c->feats, Mmax * DM));
     CA(dev_alloc(c, &c->hx, Bm * HD));
-    CA(dev_alloc(c, &c->hy, Bm * HD));
-    CA(dev_alloc(c, &c->hv, Bm * 512));
+    CA(dev_alloc(c, &c->hx2, Bm * HD));
     CA(dev_alloc(c, &c->hq, Bm * 512));
     CA(dev_alloc(c, &c->hu, Bm * 8 * DM));
-    CA(dev_alloc(c, &c->hsc, Bm * 8 * TOK));
+    {   // per-segment partial pooled contexts of the one-pass cross-attention (at most one per 16-token chunk)
+        const size_t chunks = Bm * XA_NCH;
+        CA(dev_alloc(c, &c->hpart, chunks * 8 * DM));
+        CA(dev_alloc(c, &c->hml, chunks * 16));
+        CA(dev_alloc(c, &c->hticket, Bm));
+        CA(cudaMemset(c->hticket, 0, Bm * sizeof(unsigned int)));
+    }
     CA(dev_alloc(c, &c->hpool, Bm * 8 * DM));
     CA(dev_alloc(c, &c->ho, Bm * 512));
     CA(dev_alloc(c, &c->hh, Bm * HD));
@@ -613,10 +638,18 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
               make_tmap_f32_out(&c->tm_x_out, c->x, Mmax, DM, DM) &&
               make_tmap_attn(&c->tm_att128, &c->tm_att32, c->qkv, Mmax);
     if (!ok) return bail(HM_ERR_CUDA, "activation tensor-map encoding failed");
-    const int sk_smem = SK_ROWS * SK_KMAX * (int)sizeof(float);
-    if (cudaFuncSetAttribute(skinny_linear_kernel<SK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(skinny_linear_kernel<SK_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(skinny_linear_kernel<SK_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) != cudaSuccess ||
+    const int sk_smem = SK_SMEM_MAX;
+    bool sk_ok = true;
+    auto sk_attr = [&](auto kern) { sk_ok = sk_ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem) == cudaSuccess; };
+#define SK_ATTR_ALL(CPW)                                                                                        \
+    sk_attr(skinny_linear_kernel<CPW, SK_NONE, false>); sk_attr(skinny_linear_kernel<CPW, SK_NONE, true>);     \
+    sk_attr(skinny_linear_kernel<CPW, SK_GELU, false>); sk_attr(skinny_linear_kernel<CPW, SK_GELU, true>);     \
+    sk_attr(skinny_linear_kernel<CPW, SK_RESID, false>); sk_attr(skinny_linear_kernel<CPW, SK_RESID, true>);
+    SK_ATTR_ALL(1) SK_ATTR_ALL(2) SK_ATTR_ALL(4)
+#undef SK_ATTR_ALL
+    sk_ok = sk_ok && cudaFuncSetAttribute(head_xattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XA_SMEM_BYTES) == cudaSuccess &&
+            cudaFuncSetAttribute(head_xattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XA_SMEM_BYTES) == cudaSuccess;
+    if (!sk_ok ||
         cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ATT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(vit_attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -736,7 +769,7 @@ int hm_finalize_weights(hm_ctx* c) {
         HM_CUDA(c, dev_alloc(c, &c->tok0, (size_t)HD));
         HM_CUDA(c, dev_alloc(c, &c->w_read, (size_t)NREAD * HD));
         HM_CUDA(c, dev_alloc(c, &c->b_read, (size_t)NREAD));
-        for (int l = 0; l < HDEPTH; ++l) HM_CUDA(c, dev_alloc(c, &c->w_kT[l], (size_t)8 * DM * 64));
+        for (int l = 0; l < HDEPTH; ++l) HM_CUDA(c, dev_alloc(c, &c->w_sa[l], (size_t)HD * HD));
     }
     {   // patch weight [1280,768] -> bf16 [1280, 1536] = [W | W]
         HM_CUDA(c, fetch("backbone.patch_embed.proj.weight", h));
@@ -769,14 +802,25 @@ int hm_finalize_weights(hm_ctx* c) {
         for (int i = 0; i < HD; ++i) h[i] += h2[i];
         HM_CUDA(c, cudaMemcpy(c->tok0, h.data(), HD * 4, cudaMemcpyHostToDevice));
     }
-    for (int l = 0; l < HDEPTH; ++l) {   // w_kT[h][c][d] = to_kv.weight[h*64 + d][c]
-        HM_CUDA(c, fetch(dec_name(l, 1, "fn.to_kv.weight"), h));
-        std::vector<float> kt((size_t)8 * DM * 64);
-        for (int hh = 0; hh < 8; ++hh)
-            for (int cc = 0; cc < DM; ++cc)
-                for (int d = 0; d < 64; ++d)
-                    kt[((size_t)hh * DM + cc) * 64 + d] = h[(size_t)(hh * 64 + d) * DM + cc];
-        HM_CUDA(c, cudaMemcpy(c->w_kT[l], kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
+    for (int l = 0; l < HDEPTH; ++l) {
+        // Self-attention over ONE token: softmax of a single logit is 1, so SA(y) = to_out(W_v y) = (W_o W_v) y + b_o
+        // (pose_transformer.py:55-86).  The product is formed once here in double and rounded to fp32: one 1024 x 1024
+        // matrix instead of a 512 x 1024 and a 1024 x 512 launch per layer (the rounding of the merged matrix, 6e-8
+        // relative, is below the fp32 noise of evaluating the two factors one after the other).
+        HM_CUDA(c, fetch(dec_name(l, 0, "fn.to_qkv.weight"), h));       // [1536][1024], rows 1024.. = W_v
+        HM_CUDA(c, fetch(dec_name(l, 0, "fn.to_out.0.weight"), h2));    // [1024][512]
+        std::vector<float> m((size_t)HD * HD);
+        std::vector<double> row(HD);
+        for (int n = 0; n < HD; ++n) {
+            std::fill(row.begin(), row.end(), 0.0);
+            for (int j = 0; j < 512; ++j) {
+                const double wo = h2[(size_t)n * 512 + j];
+                const float* wv = &h[(size_t)(1024 + j) * HD];
+                for (int k = 0; k < HD; ++k) row[k] += wo * (double)wv[k];
+            }
+            for (int k = 0; k < HD; ++k) m[(size_t)n * HD + k] = (float)row[k];
+        }
+        HM_CUDA(c, cudaMemcpy(c->w_sa[l], m.data(), m.size() * 4, cudaMemcpyHostToDevice));
     }
     {   // read-out: [decpose; decshape; deccam], bias + init_* (mano_head.py:93-95)
         std::vector<float> wr((size_t)NREAD * HD), br(NREAD);
@@ -822,10 +866,9 @@ int hm_finalize_weights(hm_ctx* c) {
         w.n0g = F(dec_name(l, 0, "norm.weight")); w.n0b = F(dec_name(l, 0, "norm.bias"));
         w.n1g = F(dec_name(l, 1, "norm.weight")); w.n1b = F(dec_name(l, 1, "norm.bias"));
         w.n2g = F(dec_name(l, 2, "norm.weight")); w.n2b = F(dec_name(l, 2, "norm.bias"));
-        w.w_sa_v = F(dec_name(l, 0, "fn.to_qkv.weight")) + (size_t)1024 * HD;
-        w.w_sa_o = F(dec_name(l, 0, "fn.to_out.0.weight")); w.b_sa_o = F(dec_name(l, 0, "fn.to_out.0.bias"));
+        w.w_sa = c->w_sa[l]; w.b_sa_o = F(dec_name(l, 0, "fn.to_out.0.bias"));
         w.w_q = F(dec_name(l, 1, "fn.to_q.weight"));
-        w.w_kT = c->w_kT[l];
+        w.w_k = F(dec_name(l, 1, "fn.to_kv.weight"));
         w.w_v = F(dec_name(l, 1, "fn.to_kv.weight")) + (size_t)512 * DM;
         w.w_ca_o = F(dec_name(l, 1, "fn.to_out.0.weight")); w.b_ca_o = F(dec_name(l, 1, "fn.to_out.0.bias"));
         w.w1 = F(dec_name(l, 2, "fn.net.0.weight")); w.b1 = F(dec_name(l, 2, "fn.net.0.bias"));
@@ -1129,6 +1172,86 @@ int hm_preprocess_centers(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- detector hand-off --------------------------------------------------------------------------------
+namespace {
+long py_round(double v) { return (long)nearbyint(v); }   // Python's round(): half to even (default FE_TONEAREST)
+
+// letterbox(img, new_shape, auto=True, scaleFill=False, scaleup=True, stride) geometry, yolov7/utils/datasets.py:999-1028
+bool letterbox_geom(int H, int W, int new_size, int stride, LetterboxGeom* g) {
+    if (H <= 0 || W <= 0 || new_size <= 0 || stride <= 0) return false;
+    const double r = std::min((double)new_size / H, (double)new_size / W);
+    const long uw = py_round(W * r), uh = py_round(H * r);          // new_unpad = (w, h)
+    if (uw <= 0 || uh <= 0) return false;
+    double dw = (double)(new_size - uw), dh = (double)(new_size - uh);
+    dw = fmod(dw, (double)stride); dh = fmod(dh, (double)stride);   // np.mod of non-negative values
+    dw /= 2; dh /= 2;
+    const long top = py_round(dh - 0.1), bottom = py_round(dh + 0.1), left = py_round(dw - 0.1), right = py_round(dw + 0.1);
+    g->H = H; g->W = W; g->rh = (int)uh; g->rw = (int)uw; g->top = (int)top; g->left = (int)left;
+    g->oh = (int)(uh + top + bottom); g->ow = (int)(uw + left + right);
+    g->resize = (uw != W || uh != H) ? 1 : 0;
+    g->scale_x = (double)W / (double)uw; g->scale_y = (double)H / (double)uh;   // cv::resize: inv_scale = 1 / (dsize / ssize)
+    return true;
+}
+}  // namespace
+
+int hm_letterbox_shape(int H, int W, int new_size, int stride, int32_t* out_h, int32_t* out_w) {
+    LetterboxGeom g;
+    if (!out_h || !out_w || !letterbox_geom(H, W, new_size, stride, &g)) return HM_ERR_INVALID;
+    *out_h = g.oh; *out_w = g.ow;
+    return HM_OK;
+}
+
+int hm_letterbox(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device, int new_size,
+                 int stride, int out_half, void* img_out, const uint8_t** frame_dev_out, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    LetterboxGeom g;
+    if (!frame_bgr || !img_out || row_stride < (int64_t)W * 3 || !letterbox_geom(H, W, new_size, stride, &g))
+        return fail(c, HM_ERR_INVALID, "hm_letterbox: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    const uint8_t* frame = frame_bgr;
+    if (!frame_on_device) {
+        const size_t bytes = (size_t)(H - 1) * (size_t)row_stride + (size_t)W * 3;
+        if (!c->frame_dev || bytes > (size_t)c->cfg.max_frame_bytes)
+            return fail(c, HM_ERR_INVALID, "hm_letterbox: frame larger than hm_config.max_frame_bytes");
+        if (c->crop_kernel_recorded) HM_CUDA(c, cudaStreamWaitEvent(s, c->crop_kernel_event, 0));   // frame_dev may still be read
+        HM_CUDA(c, cudaMemcpyAsync(c->frame_dev, frame_bgr, bytes, cudaMemcpyHostToDevice, s));
+        frame = c->frame_dev;
+    }
+    if (frame_dev_out) *frame_dev_out = frame;
+    const dim3 grid((g.ow + 127) / 128, g.oh);
+    if (out_half) launch_pdl(letterbox_kernel<__half>, grid, dim3(128), 0, s, frame, row_stride, g, reinterpret_cast<__half*>(img_out));
+    else launch_pdl(letterbox_kernel<float>, grid, dim3(128), 0, s, frame, row_stride, g, reinterpret_cast<float*>(img_out));
+    HM_CUDA(c, cudaGetLastError());
+    if (!frame_on_device) {
+        HM_CUDA(c, cudaEventRecord(c->crop_kernel_event, s));
+        c->crop_kernel_recorded = true;
+    }
+    return HM_OK;
+}
+
+int hm_scale_boxes(hm_ctx* c, const void* det, int det_half, int n, int det_stride, int img1_h, int img1_w, int img0_h,
+                   int img0_w, double* boxes_xyxy, uint8_t* is_right, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (n == 0) return HM_OK;
+    if (!det || !boxes_xyxy || !is_right || n < 0 || det_stride < 6 || img1_h <= 0 || img1_w <= 0 || img0_h <= 0 || img0_w <= 0)
+        return fail(c, HM_ERR_INVALID, "hm_scale_boxes: bad arguments");
+    // scale_coords, ratio_pad=None (general.py:325-327): Python double arithmetic, then used as scalars of tensor ops
+    const double gain = std::min((double)img1_h / img0_h, (double)img1_w / img0_w);
+    const double pad_x = (img1_w - img0_w * gain) / 2, pad_y = (img1_h - img0_h * gain) / 2;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    const dim3 grid((n + 127) / 128);
+    if (det_half)
+        launch_pdl(scale_boxes_kernel<__half>, grid, dim3(128), 0, s, reinterpret_cast<const __half*>(det), n, det_stride,
+                   (float)pad_x, (float)pad_y, (float)gain, (float)img0_w, (float)img0_h, boxes_xyxy, is_right);
+    else
+        launch_pdl(scale_boxes_kernel<float>, grid, dim3(128), 0, s, reinterpret_cast<const float*>(det), n, det_stride,
+                   (float)pad_x, (float)pad_y, (float)gain, (float)img0_w, (float)img0_h, boxes_xyxy, is_right);
+    HM_CUDA(c, cudaGetLastError());
+    return HM_OK;
+}
+
 int hm_profile_enable(hm_ctx* c, int on) {
     if (!c) return HM_ERR_INVALID;
     c->prof_on = on != 0;
@@ -1189,6 +1312,50 @@ __global__ void camera_postprocess_kernel(const float* __restrict__ pred_cam, fl
     }
     kp2d_full[((size_t)h * 21 + k) * 2] = u;
     kp2d_full[((size_t)h * 21 + k) * 2 + 1] = v;
+}
+
+// Rotation matrix -> axis-angle (the log map), one thread per matrix, double arithmetic.  Replaces the matrix -> vector
+// branch of cv2.Rodrigues, which the reference calls once per 3 x 3 on the host (matrix_to_axis_angle, hamer/infer.py:1082-1096,
+// 16 calls per hand).  cv2 takes r = (R32 - R23, R13 - R31, R21 - R12), s = |r| / 2, theta = acos((tr R - 1) / 2) and returns
+// r theta / (2 s): that divides the float32 rounding of R (6e-8) by sin(theta), i.e. it loses the axis near theta = pi.  Here the
+// rotation goes through its unit quaternion (largest-pivot branch, Shepperd), theta = 2 atan2(|v|, w): the same vector as cv2
+// to ~1e-7 away from pi and a vector that still reproduces R to 1e-7 next to pi (tests/test_gpu_api.py).  OpenCV's SVD
+// re-orthogonalisation of the input is not needed: the decoder's matrices are orthonormal by construction (Gram-Schmidt in
+// head_finalize_kernel).
+__global__ void rotmat_log_kernel(const float* __restrict__ R, int n, float* __restrict__ out) {
+    ptx::pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* m = R + (size_t)i * 9;
+    const double r00 = m[0], r01 = m[1], r02 = m[2], r10 = m[3], r11 = m[4], r12 = m[5], r20 = m[6], r21 = m[7], r22 = m[8];
+    const double tr = r00 + r11 + r22;
+    double w, x, y, z;
+    if (tr > 0.0) {
+        const double S = 2.0 * sqrt(tr + 1.0);
+        w = 0.25 * S; x = (r21 - r12) / S; y = (r02 - r20) / S; z = (r10 - r01) / S;
+    } else if (r00 > r11 && r00 > r22) {
+        const double S = 2.0 * sqrt(fmax(1.0 + r00 - r11 - r22, 0.0));
+        w = (r21 - r12) / S; x = 0.25 * S; y = (r01 + r10) / S; z = (r02 + r20) / S;
+    } else if (r11 > r22) {
+        const double S = 2.0 * sqrt(fmax(1.0 + r11 - r00 - r22, 0.0));
+        w = (r02 - r20) / S; x = (r01 + r10) / S; y = 0.25 * S; z = (r12 + r21) / S;
+    } else {
+        const double S = 2.0 * sqrt(fmax(1.0 + r22 - r00 - r11, 0.0));
+        w = (r10 - r01) / S; x = (r02 + r20) / S; y = (r12 + r21) / S; z = 0.25 * S;
+    }
+    if (w < 0.0) { w = -w; x = -x; y = -y; z = -z; }              // theta in [0, pi]
+    const double nv = sqrt(x * x + y * y + z * z);
+    const double k = nv > 1e-300 ? 2.0 * atan2(nv, w) / nv : 2.0;  // theta / sin(theta / 2) -> 2 as theta -> 0
+    out[(size_t)i * 3] = (float)(x * k); out[(size_t)i * 3 + 1] = (float)(y * k); out[(size_t)i * 3 + 2] = (float)(z * k);
+}
+
+int hm_rotmat_to_axis_angle(hm_ctx* c, const float* rotmats, int n, float* axis_angle, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!rotmats || !axis_angle || n <= 0) return fail(c, HM_ERR_INVALID, "hm_rotmat_to_axis_angle: bad arguments");
+    HM_CUDA(c, cudaSetDevice(c->device));
+    HM_CUDA(c, launch_pdl(rotmat_log_kernel, dim3((n + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),
+                          rotmats, n, axis_angle));
+    return HM_OK;
 }
 
 int hm_camera_postprocess(hm_ctx* c, const float* pred_cam, float* kp3d, const float* meta, int meta_stride,
@@ -1298,8 +1465,8 @@ int hm_allgather(hm_ctx* c, void* nccl_comm, const float* local_records, float* 
 
 int hm_forward_launch_count(const hm_ctx* ctx) {
     // im2col + patch GEMM + 32 x (LN, qkv, attention, proj, LN, fc1, fc2) + last LN
-    // + decoder (token init + 6 x 13 + read-out + finalize) + MANO (one fused kernel; 3 on the three-kernel path)
-    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 13 + 2) + ((ctx && (ctx->mano_legacy || !ctx->mano_fused_ok)) ? 3 : 1);
+    // + decoder (token init + 6 x 8 + read-out + finalize) + MANO (one fused kernel; 3 on the three-kernel path)
+    return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 8 + 2) + ((ctx && (ctx->mano_legacy || !ctx->mano_fused_ok)) ? 3 : 1);
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------

@@ -32,6 +32,14 @@ class _ManoHandle:
         self.faces = data['faces']
 
 
+class _DeviceFrame:
+    """A host frame that hm_letterbox uploaded into the context's frame buffer: hand it to Engine.preprocess so the crops
+    read the device copy (valid until the next host frame goes through letterbox / preprocess)."""
+
+    def __init__(self, ptr, H, W, row_stride, host):
+        self.ptr, self.shape, self.row_stride, self.host = ptr, (H, W, 3), row_stride, host
+
+
 class Engine:
     """Owns one hm_ctx (one device, one stream user).  Thin: argument marshalling only."""
 
@@ -226,7 +234,10 @@ class Engine:
         center = np.empty((n, 2), np.float32)
         size = np.empty((n,), np.float32)
         trans = np.empty((n, 2, 3), np.float32)
-        if isinstance(frame_bgr, torch.Tensor):
+        if isinstance(frame_bgr, _DeviceFrame):
+            H, W = frame_bgr.shape[:2]
+            fptr, stride, on_dev, keep = frame_bgr.ptr, frame_bgr.row_stride, 1, frame_bgr
+        elif isinstance(frame_bgr, torch.Tensor):
             assert frame_bgr.is_cuda and frame_bgr.dtype == torch.uint8 and frame_bgr.stride(-1) == 1
             H, W = frame_bgr.shape[:2]
             fptr, stride, on_dev, keep = frame_bgr.data_ptr(), frame_bgr.stride(0), 1, frame_bgr
@@ -280,6 +291,56 @@ class Engine:
                 self.h, _ptr(pred_cam.contiguous()), _ptr(kp3d), _ptr(meta), int(meta.stride(0)), int(bool(fxfy_differ)),
                 int(bool(add_center)), n, _ptr(cam_t), _ptr(kp2d), self.stream()))
         return cam_t, kp2d
+
+    def rotmat_to_axis_angle(self, rotmats):
+        """[..., 3, 3] CUDA float32 rotation matrices -> [..., 3] axis-angle vectors (cv2.Rodrigues' log map on the device)."""
+        r = rotmats.to(self.device, torch.float32).contiguous()
+        n = r.numel() // 9
+        out = torch.empty(*r.shape[:-2], 3, device=self.device, dtype=torch.float32)
+        if n:
+            with torch.cuda.device(self.device):
+                self.check(self.lib.hm_rotmat_to_axis_angle(self.h, _ptr(r), n, _ptr(out), self.stream()))
+        return out
+
+    def letterbox(self, frame_bgr, new_size=640, stride=32, half=False):
+        """LoadImage.process_img + the / 255 of Detector.detect on the device (hm_letterbox): HxWx3 uint8 BGR frame (numpy on the
+        host or a CUDA uint8 tensor) -> ([3, H', W'] CUDA float32 / float16 RGB in 0..1, the frame on the device as a CUDA
+        uint8 view).  A host frame is uploaded once; pass the returned device frame to ``preprocess`` for the crops."""
+        oh, ow = C.c_int(), C.c_int()
+        if isinstance(frame_bgr, torch.Tensor):
+            assert frame_bgr.is_cuda and frame_bgr.dtype == torch.uint8 and frame_bgr.stride(-1) == 1
+            H, W = frame_bgr.shape[:2]
+            fptr, rstride, on_dev, keep = frame_bgr.data_ptr(), frame_bgr.stride(0), 1, frame_bgr
+        else:
+            keep = np.ascontiguousarray(frame_bgr)
+            assert keep.dtype == np.uint8 and keep.ndim == 3 and keep.shape[2] == 3
+            H, W = keep.shape[:2]
+            fptr, rstride, on_dev = keep.ctypes.data, keep.strides[0], 0
+        self.check(self.lib.hm_letterbox_shape(H, W, int(new_size), int(stride), C.byref(oh), C.byref(ow)))
+        img = torch.empty(3, oh.value, ow.value, device=self.device, dtype=torch.float16 if half else torch.float32)
+        dev = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self.check(self.lib.hm_letterbox(self.h, C.c_void_p(fptr), H, W, rstride, on_dev, int(new_size), int(stride),
+                                             int(bool(half)), _ptr(img), C.byref(dev), self.stream()))
+        if on_dev:
+            return img, frame_bgr
+        return img, _DeviceFrame(dev.value, H, W, rstride, keep)
+
+    def scale_boxes(self, det, img1_shape, img0_shape):
+        """scale_coords(...).round() + labels (hm_scale_boxes): det CUDA [n, >=6] float32 / float16 (x1 y1 x2 y2 conf cls) ->
+        the reference's detection list [[label, [x1, y1, x2, y2]], ...] (one small device -> host copy)."""
+        n = det.shape[0]
+        if n == 0:
+            return []
+        assert det.is_cuda and det.dtype in (torch.float32, torch.float16) and det.stride(1) == 1 and det.shape[1] >= 6
+        boxes = torch.empty(n, 4, device=self.device, dtype=torch.float64)
+        right = torch.empty(n, device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.hm_scale_boxes(self.h, _ptr(det), int(det.dtype == torch.float16), n, int(det.stride(0)),
+                                               int(img1_shape[0]), int(img1_shape[1]), int(img0_shape[0]), int(img0_shape[1]),
+                                               _ptr(boxes), _ptr(right), self.stream()))
+        b, r = boxes.cpu().tolist(), right.cpu().tolist()
+        return [['right' if r[i] else 'left', b[i]] for i in range(n)]
 
     def launch_count(self):
         return int(self.lib.hm_forward_launch_count(self.h))

@@ -213,3 +213,125 @@ def save_image_results(output_folder, file_name, image_results):
     path = os.path.join(output_folder, f'{file_name}.npy')
     np.save(path, image_results)
     return path
+
+
+# -- per-hand npz (process_batch, infer.py:908-1036) ------------------------------------------------
+def save_hand_npz(output_folder, file_name, output, index, hand_label, saved_counts):
+    """One ``{stem}_{label}[_{k}].npz`` per detected hand exactly as process_batch writes it (infer.py:1003-1025):
+    betas (1,10), global_orient (1,1,3,3), hand_pose (1,15,3,3), cam_t (1,3) = pred_cam_t_full, is_right (1,) bool
+    (= do_flip == 0, infer.py:968); a second hand with the same label gets the suffix ``_2`` (infer.py:1003-1006)."""
+    mp = output['pred_mano_params']
+    sl = slice(index, index + 1)
+    suffix = f'_{hand_label}'
+    if saved_counts[hand_label] > 0:
+        suffix += f'_{saved_counts[hand_label] + 1}'
+    os.makedirs(output_folder, exist_ok=True)
+    path = os.path.join(output_folder, f'{file_name}{suffix}.npz')
+    np.savez(path,
+             betas=mp['betas'][sl].detach().cpu().numpy(),
+             global_orient=mp['global_orient'][sl].detach().cpu().numpy(),
+             hand_pose=mp['hand_pose'][sl].detach().cpu().numpy(),
+             cam_t=output['pred_cam_t_full'][sl].detach().cpu().numpy(),
+             is_right=(output['do_flip'][sl] == 0).detach().cpu().numpy())
+    saved_counts[hand_label] += 1
+    return path
+
+
+def process_image_npz(hamer, image, detection_list, output_folder, file_name, k_real=None):
+    """Inner loop of process_batch (infer.py:955-1030) for one image, batched over its hands."""
+    if not detection_list:
+        return []
+    output, _ = hamer.estimate_from_rgb(image, list(detection_list), k_real)
+    saved = {'left': 0, 'right': 0}
+    return [save_hand_npz(output_folder, file_name, output, i, bbox[0], saved) for i, bbox in enumerate(detection_list)]
+
+
+# -- device log map for the npy records --------------------------------------------------------------
+def hand_records_device(engine, output, labels):
+    """The dicts of hand_record() for every hand of ``output`` with the axis-angle vectors computed on the device
+    (hm_rotmat_to_axis_angle: one launch and one small copy for all hands instead of 16 cv2.Rodrigues calls per hand)."""
+    mp = output['pred_mano_params']
+    B = mp['betas'].shape[0]
+    rot = torch.cat([mp['global_orient'].reshape(B, 1, 3, 3), mp['hand_pose'].reshape(B, 15, 3, 3)], dim=1)
+    aa = engine.rotmat_to_axis_angle(rot).reshape(B, 48).cpu().numpy()
+    betas = mp['betas'].detach().cpu().numpy()
+    cam_t = output['pred_cam_t_full'].detach().cpu().numpy()
+    return [{'betas': betas[i], 'theta': aa[i].copy(), 'pose_hand': aa[i, 3:].copy(), 'pose_global': aa[i, :3].copy(),
+             'cam_t': cam_t[i], 'is_right': labels[i] == 'right'} for i in range(B)]
+
+
+# -- OBJ reconstruction from the npy records (reconstruct_and_save_obj_with_wrapper, infer.py:1321-1436) --------------
+def axis_angle_to_rotation_matrix_torch(rvec_tensor):
+    """infer.py:65-82 (batch Rodrigues with theta = |r| + 1e-8)."""
+    theta = torch.norm(rvec_tensor, dim=1, keepdim=True) + 1e-8
+    r_hat = rvec_tensor / theta
+    cos = torch.cos(theta)
+    z = torch.zeros(theta.shape[0], dtype=rvec_tensor.dtype, device=rvec_tensor.device)
+    m = torch.stack([z, -r_hat[:, 2], r_hat[:, 1], r_hat[:, 2], z, -r_hat[:, 0], -r_hat[:, 1], r_hat[:, 0], z], dim=1).reshape(-1, 3, 3)
+    eye = torch.eye(3, dtype=rvec_tensor.dtype, device=rvec_tensor.device).unsqueeze(0).expand(rvec_tensor.shape[0], -1, -1)
+    A = r_hat.unsqueeze(2) * r_hat.unsqueeze(1)
+    return cos.unsqueeze(2) * eye + (1 - cos.unsqueeze(2)) * A + torch.sin(theta).unsqueeze(2) * m
+
+
+RIGHT_COLOR, LEFT_COLOR = (100, 200, 100, 255), (200, 100, 100, 255)     # infer.py:1405, 1416
+
+
+def hand_meshes_from_record(engine, faces, data):
+    """Vertices / faces / colour of the hands of one npy record, as infer.py:1350-1421 builds them: axis-angle -> matrices,
+    MANO forward (hm_mano_lbs), + cam_t; left hands get x negated and the face winding flipped.  Hands in the reference's
+    order ('right', then 'left')."""
+    dev = engine.device
+    todo = [(t, data[t]) for t in ('right', 'left') if data.get(t) is not None]
+    if not todo:
+        return []
+    betas = torch.stack([torch.as_tensor(np.asarray(d['betas']).reshape(10), dtype=torch.float32) for _, d in todo]).to(dev)
+    aa = torch.stack([torch.cat([torch.as_tensor(np.asarray(d['pose_global']).reshape(1, 3), dtype=torch.float32),
+                                 torch.as_tensor(np.asarray(d['pose_hand']).reshape(15, 3), dtype=torch.float32)]) for _, d in todo]).to(dev)
+    rot = axis_angle_to_rotation_matrix_torch(aa.reshape(-1, 3)).reshape(len(todo), 16, 3, 3).contiguous()
+    verts, _ = engine.mano_lbs(betas, rot)
+    verts = verts.cpu().numpy()
+    out = []
+    for i, (_, d) in enumerate(todo):
+        v = verts[i].copy()
+        f = np.asarray(faces).astype(np.int32)
+        cam_t = np.asarray(d['cam_t'], dtype=v.dtype).reshape(3)
+        if d['is_right']:
+            v += cam_t
+            color = RIGHT_COLOR
+        else:
+            v[:, 0] = -v[:, 0]
+            f = f[:, [0, 2, 1]]
+            v += cam_t                                   # (the reference's "Tx flip" is a no-op: real_cam_t[0] = real_cam_t[0])
+            color = LEFT_COLOR
+        out.append((v, f, color))
+    return out
+
+
+def write_obj(path, meshes):
+    """Concatenated Wavefront OBJ of (vertices, faces, rgba) meshes with per-vertex colours (``v x y z r g b``, colours
+    in [0, 1]) - the layout trimesh's exporter gives a vertex-coloured mesh (trimesh itself is not a dependency here)."""
+    lines, base = ['# hamer_yolo_b200 (layout of trimesh.exchange.obj.export_obj)'], 0
+    for v, f, color in meshes:
+        r, g, b = (c / 255.0 for c in color[:3])
+        lines += [f'v {x:.8f} {y:.8f} {z:.8f} {r:.8f} {g:.8f} {b:.8f}' for x, y, z in v]
+    for v, f, color in meshes:
+        lines += [f'f {a + 1 + base} {b_ + 1 + base} {c + 1 + base}' for a, b_, c in f]
+        base += len(v)
+    with open(path, 'w') as fh:
+        fh.write('\n'.join(lines) + '\n')
+    return path
+
+
+def reconstruct_and_save_obj_with_wrapper(npy_folder, output_obj_folder, hamer_instance):
+    """infer.py:1321-1436: every ``*.npy`` record of ``npy_folder`` becomes ``{stem}.obj`` (both hands in one file)."""
+    import glob
+    os.makedirs(output_obj_folder, exist_ok=True)
+    model = hamer_instance.model if hasattr(hamer_instance, 'model') else hamer_instance
+    written = []
+    for npy_path in sorted(glob.glob(os.path.join(npy_folder, '*.npy'))):
+        stem = os.path.splitext(os.path.basename(npy_path))[0]
+        data = np.load(npy_path, allow_pickle=True).item()
+        meshes = hand_meshes_from_record(model.engine, model.mano.faces, data)
+        if meshes:
+            written.append(write_obj(os.path.join(output_obj_folder, f'{stem}.obj'), meshes))
+    return written

@@ -146,6 +146,33 @@ int hm_mano_lbs(hm_ctx* ctx, const float* betas, const float* rotmats, const flo
 int hm_camera_postprocess(hm_ctx* ctx, const float* pred_cam, float* kp3d, const float* meta, int meta_stride,
                           int fxfy_differ, int add_center, int n, float* cam_t_full, float* kp2d_full, void* stream);
 
+/* ---- detector hand-off on the device (the YOLOv7 detector itself stays upstream) --------------------------------------
+ * hm_letterbox replaces LoadImage.process_img (yolo/yolov7/utils/datasets.py:137-141: letterbox(img0, new_size, stride,
+ * auto=True), datasets.py:999-1030 = cv2.resize INTER_LINEAR + cv2.copyMakeBorder 114; BGR -> RGB; HWC -> CHW) and the
+ * uint8 -> float / 255 of Detector.detect (yolo/detector.py:121-123), bit for bit:
+ *   frame_bgr : H x W x 3 uint8 BGR, host unless frame_on_device != 0 (a host frame is uploaded whole into the context's
+ *               frame buffer - hm_config.max_frame_bytes - and *frame_dev_out, if not NULL, receives the device copy so
+ *               that the following hm_preprocess can run with frame_on_device = 1: the frame crosses PCIe once)
+ *   img_out   : DEVICE [3, out_h, out_w] float32 (out_half = 0) or float16 (out_half = 1), RGB, 0..1;
+ *               hm_letterbox_shape gives (out_h, out_w) for H, W, new_size (640), stride (32).
+ * hm_scale_boxes replaces scale_coords(img.shape[2:], det[:, :4], im0.shape).round() and the right / left labelling
+ * (yolo/detector.py:139-145, yolov7/utils/general.py:323-345) in the detections' own precision:
+ *   det       : DEVICE [n, det_stride] float32 / float16 rows x1 y1 x2 y2 conf cls (non_max_suppression output)
+ *   boxes_xyxy: DEVICE [n,4] float64, is_right: DEVICE [n] (cls == 1) - after one small copy, the arguments of hm_preprocess. */
+int hm_letterbox_shape(int H, int W, int new_size, int stride, int32_t* out_h, int32_t* out_w);
+int hm_letterbox(hm_ctx* ctx, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device, int new_size,
+                 int stride, int out_half, void* img_out, const uint8_t** frame_dev_out, void* stream);
+int hm_scale_boxes(hm_ctx* ctx, const void* det, int det_half, int n, int det_stride, int img1_h, int img1_w, int img0_h,
+                   int img0_w, double* boxes_xyxy, uint8_t* is_right, void* stream);
+
+/* hm_rotmat_to_axis_angle replaces matrix_to_axis_angle (hamer/infer.py:1082-1096: cv2.Rodrigues per 3 x 3 on the host, 16
+ * calls per hand) for the npy writer's 'theta' / 'pose_hand' / 'pose_global' (infer.py:1279-1303): rotmats DEVICE [n,3,3]
+ * float32 -> axis_angle DEVICE [n,3] float32, double arithmetic inside (through the unit quaternion: well conditioned up to
+ * theta = pi, where cv2's r theta / (2 sin theta) amplifies the float32 rounding of R); agrees with cv2.Rodrigues to ~1e-6 rad
+ * away from pi (cv2's SVD re-orthogonalisation of the input is skipped - the decoder's matrices are orthonormal by
+ * construction). */
+int hm_rotmat_to_axis_angle(hm_ctx* ctx, const float* rotmats, int n, float* axis_angle, void* stream);
+
 /* ---- multi-GPU --------------------------------------------------------------------------------
  * The reference runs one process and one hand at a time (hamer/infer.py:1268-1274); crops are independent, so the path
  * shards data-parallel: one context per rank / GPU, each rank runs hm_forward on its crops, and ONE collective gathers the

@@ -238,3 +238,103 @@ def test_allgather_entry_point_single_rank(model):
     from hamer_yolo_b200._lib import HmError
     with pytest.raises(HmError):
         eng.check(eng.lib.hm_allgather(eng.h, None, C.c_void_p(rec.data_ptr()), C.c_void_p(out.data_ptr()), 5, eng.stream()))
+
+
+def test_device_log_map_matches_cv2_rodrigues(model):
+    """hm_rotmat_to_axis_angle against cv2.Rodrigues (what matrix_to_axis_angle calls per 3 x 3, infer.py:1082-1096),
+    including rotations near 0 and near pi."""
+    import cv2
+    from oracle.head import rot6d_to_rotmat
+    g = torch.Generator().manual_seed(5)
+    R = rot6d_to_rotmat(torch.randn(500, 6, generator=g))
+    axis = torch.nn.functional.normalize(torch.randn(6, 3, generator=g), dim=1)
+    special = []
+    for k, ang in enumerate([0.0, 1e-7, 1e-4, np.pi - 1e-7, np.pi - 1e-4, 3.0]):
+        special.append(torch.from_numpy(cv2.Rodrigues((axis[k] * ang).numpy().astype(np.float64))[0]).float())
+    R = torch.cat([R, torch.stack(special)])
+    aa = model.engine.rotmat_to_axis_angle(R.cuda()).cpu().numpy()
+    ref = np.stack([cv2.Rodrigues(m.numpy())[0].reshape(3) for m in R])
+    # compare as rotations (near pi the axis sign is a convention) and as vectors away from pi
+    back = np.stack([cv2.Rodrigues(v.astype(np.float64))[0] for v in aa])
+    assert np.abs(back - R.numpy()).max() < 2e-6
+    ang = np.linalg.norm(ref, axis=1)
+    ok = ang < np.pi - 1e-3
+    assert np.abs(aa[ok] - ref[ok]).max() < 5e-6
+
+
+def test_npz_and_obj_writers(model, tmp_path):
+    """process_batch's per-hand npz (infer.py:1003-1025), the device log-map npy records and the OBJ reconstruction from
+    the npy (infer.py:1321-1436): the OBJ vertices must equal MANO(axis-angle of the record) + cam_t, left hands mirrored."""
+    from hamer_yolo_b200 import hamer_inference
+    from hamer_yolo_b200 import inference as hi_mod
+    from oracle.mano import mano_forward
+    hi = hamer_inference(model=model)
+    frame = synthetic_frame(480, 640, 14)
+    dets = [['right', [100, 80, 260, 300]], ['left', [330, 120, 520, 420]], ['right', [20, 200, 150, 380]]]
+    paths = hi_mod.process_image_npz(hi, frame, dets, str(tmp_path / 'npz'), 'img0')
+    assert [p.split('/')[-1] for p in paths] == ['img0_right.npz', 'img0_left.npz', 'img0_right_2.npz']
+    z = np.load(paths[1])
+    assert z['betas'].shape == (1, 10) and z['global_orient'].shape == (1, 1, 3, 3) and z['hand_pose'].shape == (1, 15, 3, 3)
+    assert z['cam_t'].shape == (1, 3) and z['is_right'].shape == (1,) and not z['is_right'][0] and np.load(paths[0])['is_right'][0]
+    # npy records: device log map vs the host cv2 path
+    out, _ = hi.estimate_from_rgb(frame, dets)
+    recs = hi_mod.hand_records_device(model.engine, out, [d[0] for d in dets])
+    for i, d in enumerate(dets):
+        ref = hi_mod.hand_record(out, i, d[0] == 'right')
+        assert set(recs[i]) == set(ref) and recs[i]['is_right'] == ref['is_right']
+        assert np.abs(recs[i]['theta'] - ref['theta']).max() < 5e-6 and np.array_equal(recs[i]['betas'], ref['betas'])
+    npy_dir = tmp_path / 'npy'
+    hi_mod.save_image_results(str(npy_dir), 'img0', {'left': recs[1], 'right': recs[0]})
+    objs = hi_mod.reconstruct_and_save_obj_with_wrapper(str(npy_dir), str(tmp_path / 'obj'), hi)
+    assert len(objs) == 1
+    vs = np.array([[float(x) for x in l.split()[1:4]] for l in open(objs[0]) if l.startswith('v ')])
+    fs = np.array([[int(x) for x in l.split()[1:4]] for l in open(objs[0]) if l.startswith('f ')])
+    assert vs.shape == (2 * 778, 3) and fs.shape == (2 * 1538, 3) and fs.min() == 1 and fs.max() == 2 * 778
+    mano = model.mano.data
+    for k, rec in enumerate((recs[0], recs[1])):                 # right first, then left (infer.py:1354)
+        aa = torch.from_numpy(np.concatenate([rec['pose_global'], rec['pose_hand']]).reshape(16, 3)).float()
+        R = hi_mod.axis_angle_to_rotation_matrix_torch(aa).reshape(1, 16, 3, 3)
+        v_ref, _ = mano_forward(R[:, :1], R[:, 1:], torch.from_numpy(rec['betas']).reshape(1, 10), mano)
+        v_ref = v_ref[0].numpy().copy()
+        if not rec['is_right']:
+            v_ref[:, 0] = -v_ref[:, 0]
+        v_ref += rec['cam_t']
+        assert np.abs(vs[k * 778:(k + 1) * 778] - v_ref).max() < 5e-5
+    assert np.array_equal(fs[1538:] - 778, np.asarray(model.mano.faces)[:, [0, 2, 1]] + 1)
+
+
+@pytest.mark.parametrize('h,w', [(1080, 1920), (480, 640), (240, 320), (640, 360), (333, 517), (384, 640)])
+@pytest.mark.parametrize('half', [False, True])
+def test_letterbox_matches_the_yolo_loader(model, h, w, half):
+    """hm_letterbox against LoadImage.process_img + Detector.detect's tensor conversion (cv2.resize / copyMakeBorder through the
+    oracle): bit-identical, down- and up-scaling, host and device frames."""
+    from oracle import letterbox as ol
+    frame = synthetic_frame(h, w, h + w)
+    ref = ol.process_img(frame, 640, 32, half=half)
+    img, dev_frame = model.engine.letterbox(frame, 640, 32, half=half)
+    assert img.shape == ref.shape and img.dtype == ref.dtype
+    assert torch.equal(img.cpu(), ref)
+    img2, _ = model.engine.letterbox(torch.from_numpy(frame).cuda(), 640, 32, half=half)
+    assert torch.equal(img2.cpu(), ref)
+    # the uploaded frame feeds the crop kernel without a second host -> device copy
+    from oracle import crop as oc
+    dets = [['right', [w * 0.2, h * 0.2, w * 0.5, h * 0.6]], ['left', [w * 0.55, h * 0.3, w * 0.9, h * 0.8]]]
+    crops, _, _, _ = model.engine.preprocess(dev_frame, [d[1] for d in dets], [1, 0])
+    assert torch.equal(crops.cpu(), torch.from_numpy(oc.prepare_batch_bbox(frame, dets)['img']))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_scale_boxes_matches_scale_coords(model, dtype):
+    """hm_scale_boxes against scale_coords(...).round() + the labelling of Detector.detect, in the detections' own dtype."""
+    from oracle import letterbox as ol
+    g = torch.Generator().manual_seed(3)
+    for (h, w) in [(1080, 1920), (480, 640), (517, 333)]:
+        oh = ol.process_img(np.zeros((h, w, 3), np.uint8)).shape
+        n = 37
+        xy1 = torch.rand(n, 2, generator=g) * torch.tensor([oh[2] * 0.8, oh[1] * 0.8]) - 5.0
+        wh = torch.rand(n, 2, generator=g) * 200 + 2
+        det = torch.cat([xy1, xy1 + wh, torch.rand(n, 1, generator=g), torch.randint(0, 2, (n, 1), generator=g).float()], 1).to(dtype)
+        ref = ol.detections_to_list(det.cuda() if dtype == torch.float16 else det, oh[1:], (h, w, 3))
+        got = model.engine.scale_boxes(det.cuda(), oh[1:], (h, w, 3))
+        assert got == ref
+    assert model.engine.scale_boxes(torch.zeros(0, 6).cuda(), (384, 640), (1080, 1920, 3)) == []
