@@ -31,7 +31,7 @@ class HmError(RuntimeError):
 
 # every symbol include/hamer_b200.h declares (tests check the library exports all of them)
 EXPORTS = ('hm_create', 'hm_destroy', 'hm_last_error', 'hm_set_weight', 'hm_finalize_weights',
-           'hm_set_mano', 'hm_preprocess', 'hm_preprocess_centers', 'hm_forward', 'hm_backbone', 'hm_mano_head',
+           'hm_set_mano', 'hm_preprocess', 'hm_preprocess_centers', 'hm_preprocess_blur', 'hm_forward', 'hm_backbone', 'hm_mano_head',
            'hm_mano_lbs', 'hm_camera_postprocess', 'hm_rotmat_to_axis_angle', 'hm_letterbox_shape', 'hm_letterbox', 'hm_scale_boxes', 'hm_comm_unique_id', 'hm_comm_init', 'hm_comm_destroy', 'hm_allgather', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
            'hm_profile_collect', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention', 'hm_test_mano_clocks')
 
@@ -61,6 +61,7 @@ def load():
     lib.hm_set_mano.argtypes = [vp] + [vp] * 8
     lib.hm_preprocess.argtypes = [vp, vp, i32, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.hm_preprocess_centers.argtypes = [vp, vp, i32, i32, i64, i32, vp, vp, i32, vp, vp, vp]
+    lib.hm_preprocess_blur.argtypes = [vp, vp, i32, i32, i64, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.hm_forward.argtypes = [vp, vp, i32, C.POINTER(HmOutputs), vp]
     lib.hm_backbone.argtypes = [vp, vp, i32, vp, vp]
     lib.hm_mano_head.argtypes = [vp, vp, i32, C.POINTER(HmOutputs), vp]

@@ -144,6 +144,9 @@ struct hm_ctx {
     std::vector<std::array<long, 4>> crop_rect;
     CropParams* crop_host = nullptr;   // pinned
     CropParams* crop_dev = nullptr;
+    BlurParams* blur_host = nullptr;   // pinned; anti-aliased crops (hm_preprocess_blur)
+    BlurParams* blur_dev = nullptr;
+    float lut_mean[3] = {}, lut_sd[3] = {};   // float32 normalisation constants (RGB), the ones the LUT is built from
     float* lut = nullptr;              // [3][256]
     cudaEvent_t crop_event = nullptr;
     bool crop_event_pending = false;
@@ -607,6 +610,8 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     CA(dev_alloc(c, &c->hbetas, Bm * 10));
     CA(dev_alloc(c, &c->hscratch, Bm * 160));
     CA(dev_alloc(c, &c->crop_dev, Bm));
+    CA(dev_alloc(c, &c->blur_dev, Bm));
+    CA(cudaMallocHost(reinterpret_cast<void**>(&c->blur_host), Bm * sizeof(BlurParams)));
     CA(dev_alloc(c, &c->lut, (size_t)768));
     if (cfg->max_frame_bytes > 0) CA(dev_alloc(c, &c->frame_dev, (size_t)cfg->max_frame_bytes));
     CA(cudaMallocHost(reinterpret_cast<void**>(&c->crop_host), Bm * sizeof(CropParams)));
@@ -626,6 +631,7 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
         float lut[768];
         for (int ch = 0; ch < 3; ++ch) {
             const float m = (float)(255. * mean[ch]), sd = (float)(255. * stdv[ch]);
+            c->lut_mean[ch] = m; c->lut_sd[ch] = sd;
             for (int v = 0; v < 256; ++v) lut[ch * 256 + v] = ((float)v - m) / sd;
         }
         if (cudaMemcpy(c->lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -674,6 +680,7 @@ void hm_destroy(hm_ctx* c) {
     for (void* p : c->mano_allocs) cudaFree(p);
     for (auto& kv : c->w) { cudaFree(kv.second.f32); cudaFree(kv.second.bf16); }
     if (c->crop_host) cudaFreeHost(c->crop_host);
+    if (c->blur_host) cudaFreeHost(c->blur_host);
     if (c->crop_event) cudaEventDestroy(c->crop_event);
     if (c->crop_kernel_event) cudaEventDestroy(c->crop_kernel_event);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -1064,7 +1071,8 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
 // Common body of hm_preprocess / hm_preprocess_centers: ccs = [n][cx, cy, size] of the square source windows (for mode 2
 // cx is given in the mirrored image), mode 0 = plain, 1 = mirror the patch after the warp, 2 = sample the mirrored image.
 static int preprocess_impl(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
-                           const double* ccs, const uint8_t* mode, int n, float* img_out, float* trans, cudaStream_t s) {
+                           const double* ccs, const uint8_t* mode, int n, float* img_out, float* trans, cudaStream_t s,
+                           const int32_t* blur_radius = nullptr, const double* blur_weights = nullptr) {
     HM_CUDA(c, cudaSetDevice(c->device));
     if (c->crop_event_pending) {   // pinned staging still owned by the previous call's copy?
         HM_CUDA(c, cudaEventSynchronize(c->crop_event));
@@ -1074,19 +1082,30 @@ static int preprocess_impl(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, in
     // overwrite them while the previous call's crop kernel still reads them (no-op on the same stream)
     if (c->crop_kernel_recorded) HM_CUDA(c, cudaStreamWaitEvent(s, c->crop_kernel_event, 0));
     double band_lo = (double)H, band_hi = -1.0;   // source rows any crop can read (host frames: only these are uploaded)
+    bool any_blur = false;
     for (int i = 0; i < n; ++i) {
         const double cx = ccs[3 * i], cy = ccs[3 * i + 1], size = ccs[3 * i + 2];
         if (!(size > 0)) return fail(c, HM_ERR_INVALID, "hm_preprocess: empty box");
         if (mode[i] > 2) return fail(c, HM_ERR_INVALID, "hm_preprocess: bad crop mode");
         double M[6];
         center_to_affine(cx, cy, size, M);
-        if (cy - 0.5 * size < band_lo) band_lo = cy - 0.5 * size;
-        if (cy + 0.5 * size > band_hi) band_hi = cy + 0.5 * size;
+        // anti-aliased crops read the blur's support around every tap
+        const int br = blur_radius ? blur_radius[i] : 0;
+        if (br < 0 || br > CROP_BLUR_MAX_R) return fail(c, HM_ERR_INVALID, "hm_preprocess_blur: radius outside [0, 32]");
+        c->blur_host[i].radius = br;
+        c->blur_host[i].pad = 0;
+        if (br > 0) {
+            any_blur = true;
+            for (int k = 0; k <= CROP_BLUR_MAX_R; ++k) c->blur_host[i].w[k] = k <= br ? blur_weights[(size_t)i * (CROP_BLUR_MAX_R + 1) + k] : 0.0;
+        }
+        const double half = 0.5 * size + (double)br;
+        if (cy - half < band_lo) band_lo = cy - half;
+        if (cy + half > band_hi) band_hi = cy + half;
         // columns of the ORIGINAL frame the crop reads (mode 2 samples column W - 1 - x)
-        const double xa = cx - 0.5 * size, xb = cx + 0.5 * size;
+        const double xa = cx - half, xb = cx + half;
         c->crop_win[i][0] = mode[i] == 2 ? (double)(W - 1) - xb : xa;
         c->crop_win[i][1] = mode[i] == 2 ? (double)(W - 1) - xa : xb;
-        c->crop_win[i][2] = cy - 0.5 * size; c->crop_win[i][3] = cy + 0.5 * size;
+        c->crop_win[i][2] = cy - half; c->crop_win[i][3] = cy + half;
         invert_affine(M, c->crop_host[i].m);
         c->crop_host[i].flip = mode[i];
         c->crop_host[i].pad = 0;
@@ -1128,13 +1147,25 @@ static int preprocess_impl(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, in
         frame = c->frame_dev;
     }
     HM_CUDA(c, cudaMemcpyAsync(c->crop_dev, c->crop_host, (size_t)n * sizeof(CropParams), cudaMemcpyHostToDevice, s));
-    HM_CUDA(c, cudaEventRecord(c->crop_event, s));
-    c->crop_event_pending = true;
+    if (!any_blur) {       // (with blurred crops the event follows the second staging copy, below)
+        HM_CUDA(c, cudaEventRecord(c->crop_event, s));
+        c->crop_event_pending = true;
+    }
     {
         ProfScope ps(c, s, PC_CROP);
         launch_pdl(crop_warp_normalize_kernel, dim3(256, n), dim3(256), 0, s, frame, H, W, row_stride, c->crop_dev, c->lut, img_out);
+        if (any_blur) {    // the anti-aliased crops are overwritten by the float path
+            HM_CUDA(c, cudaMemcpyAsync(c->blur_dev, c->blur_host, (size_t)n * sizeof(BlurParams), cudaMemcpyHostToDevice, s));
+            launch_pdl(crop_warp_blur_kernel, dim3(256, n), dim3(256), 0, s, frame, H, W, row_stride, (const CropParams*)c->crop_dev,
+                       (const BlurParams*)c->blur_dev, make_float3(c->lut_mean[0], c->lut_mean[1], c->lut_mean[2]),
+                       make_float3(c->lut_sd[0], c->lut_sd[1], c->lut_sd[2]), img_out);
+        }
     }
     HM_CUDA(c, cudaGetLastError());
+    if (any_blur) {
+        HM_CUDA(c, cudaEventRecord(c->crop_event, s));
+        c->crop_event_pending = true;
+    }
     HM_CUDA(c, cudaEventRecord(c->crop_kernel_event, s));
     c->crop_kernel_recorded = true;
     return HM_OK;
@@ -1170,6 +1201,18 @@ int hm_preprocess_centers(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int
     if (n <= 0 || n > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_preprocess_centers: n out of range");
     return preprocess_impl(c, frame_bgr, H, W, row_stride, frame_on_device, center_size, mode, n, img_out, trans,
                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hm_preprocess_blur(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
+                       const double* center_size, const uint8_t* mode, const int32_t* blur_radius, const double* blur_weights,
+                       int n, float* img_out, float* trans, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!frame_bgr || !center_size || !mode || !blur_radius || !blur_weights || !img_out || H <= 0 || W <= 0 ||
+        row_stride < (int64_t)W * 3)
+        return fail(c, HM_ERR_INVALID, "hm_preprocess_blur: bad arguments");
+    if (n <= 0 || n > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_preprocess_blur: n out of range");
+    return preprocess_impl(c, frame_bgr, H, W, row_stride, frame_on_device, center_size, mode, n, img_out, trans,
+                           reinterpret_cast<cudaStream_t>(stream), blur_radius, blur_weights);
 }
 
 // ---- detector hand-off --------------------------------------------------------------------------------

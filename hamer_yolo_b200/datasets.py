@@ -8,8 +8,8 @@ Differences from ``prepare_batch_bbox`` that this class reproduces (they change 
     ``c_x = img_width - c_x - 1`` (hamer/hamer/datasets/utils.py:347-349) - one output column away from flipping the
     patch afterwards;
   * boxes whose crop window exceeds 2.2 x the patch (bbox_size > 563 px) are anti-aliased with a gaussian blur of the
-    WHOLE frame first (vitdet_dataset.py:62-71, skimage.filters.gaussian): not implemented here, such items raise
-    NotImplementedError (prepare_batch_bbox, the path infer.py runs, has the blur commented out).
+    WHOLE frame first (vitdet_dataset.py:62-71, skimage.filters.gaussian) and the float64 result is warped: hm_preprocess_blur
+    evaluates the same blur at the taps the warp reads, with scipy's arithmetic (csrc/crop_warp.cuh).
 
 (In the reference fork the class itself is broken - it unpacks two values from the three-value return of
 generate_image_patch_cv2, vitdet_dataset.py:74 vs datasets/utils.py:376 - so this follows what the code computes up to
@@ -80,20 +80,19 @@ class ViTDetDataset(torch.utils.data.Dataset):
         W = frame.shape[1]
         ccs = np.empty((len(indices), 3), np.float64)
         modes = np.zeros(len(indices), np.uint8)
+        sigmas = [0.0] * len(indices)          # kept as computed (numpy float32): scipy's kernel depends on the type
         sizes = []
         for n, idx in enumerate(indices):
             c_x, c_y, bbox_size, flip = self._window(idx)
             downsampling_factor = (bbox_size * 1.0) / self.img_size / 2.0
-            if downsampling_factor > 1.1:                        # vitdet_dataset.py:62-71
-                raise NotImplementedError(
-                    f'bbox_size {bbox_size:.0f} px > 563 px: the reference blurs the whole frame with skimage.filters.gaussian '
-                    f'(sigma {(downsampling_factor - 1) / 2:.3f}) and warps the float64 result - not available in this build')
+            if downsampling_factor > 1.1:                        # vitdet_dataset.py:62-71: gaussian(cvimg, sigma=(f - 1) / 2)
+                sigmas[n] = (downsampling_factor - 1) / 2
             if flip:
                 c_x = W - c_x - 1                                 # datasets/utils.py:347-349
                 modes[n] = 2
             ccs[n] = (float(c_x), float(c_y), float(bbox_size))
             sizes.append(bbox_size)
-        img, trans = self.engine.preprocess_centers(frame, ccs, modes)
+        img, trans = self.engine.preprocess_centers(frame, ccs, modes, blur_sigma=sigmas)
         return img, sizes
 
     def __getitem__(self, idx):

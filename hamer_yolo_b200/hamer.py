@@ -32,6 +32,25 @@ class _ManoHandle:
         self.faces = data['faces']
 
 
+BLUR_MAX_RADIUS = 32          # HM_BLUR_MAX_RADIUS (include/hamer_b200.h)
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    """(radius, weights[33]) of skimage.filters.gaussian / scipy.ndimage.gaussian_filter1d for ``sigma``: radius =
+    int(truncate * sigma + 0.5), weights[k] = exp(-0.5 k^2 / sigma^2) / sum - scipy's _gaussian_kernel1d, evaluated with numpy
+    as scipy does so that the taps are the reference's to the last bit."""
+    radius = int(truncate * float(sigma) + 0.5)
+    if radius > BLUR_MAX_RADIUS:
+        raise ValueError(f'anti-alias sigma {float(sigma):.2f} needs radius {radius} > {BLUR_MAX_RADIUS}')
+    sigma2 = sigma * sigma            # in sigma's own type, like scipy: ViTDetDataset passes a numpy float32
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / sigma2 * x ** 2)
+    phi = phi / phi.sum()
+    w = np.zeros(BLUR_MAX_RADIUS + 1, np.float64)
+    w[:radius + 1] = phi[radius:]
+    return radius, w
+
+
 class _DeviceFrame:
     """A host frame that hm_letterbox uploaded into the context's frame buffer: hand it to Engine.preprocess so the crops
     read the device copy (valid until the next host frame goes through letterbox / preprocess)."""
@@ -253,12 +272,21 @@ class Engine:
                 C.c_void_p(size.ctypes.data), C.c_void_p(trans.ctypes.data), self.stream()))
         return img, center, size, trans
 
-    def preprocess_centers(self, frame_bgr, center_size, modes, out=None):
+    def preprocess_centers(self, frame_bgr, center_size, modes, out=None, blur_sigma=None):
         """Crop windows given directly: center_size [n,3] float64 (c_x, c_y, size), modes [n] uint8 (0 plain, 1 mirror the
-        patch, 2 warp the mirrored frame - include/hamer_b200.h hm_preprocess_centers).  Returns (img, trans)."""
+        patch, 2 warp the mirrored frame - include/hamer_b200.h hm_preprocess_centers).  blur_sigma [n] (0 = none): the
+        anti-alias gaussian of ViTDetDataset / prepare_item applied to the frame before the warp (hm_preprocess_blur).
+        Returns (img, trans)."""
         ccs = np.ascontiguousarray(center_size, dtype=np.float64).reshape(-1, 3)
         n = ccs.shape[0]
         md = np.ascontiguousarray(modes, dtype=np.uint8).reshape(-1)
+        radius = weights = None
+        if blur_sigma is not None and any(float(sg) > 0 for sg in blur_sigma):
+            radius = np.zeros(n, np.int32)
+            weights = np.zeros((n, BLUR_MAX_RADIUS + 1), np.float64)
+            for i, sg in enumerate(blur_sigma):
+                if float(sg) > 0:
+                    radius[i], weights[i] = gaussian_taps(sg)
         img = out if out is not None else torch.empty(n, 3, IMG, IMG, device=self.device, dtype=torch.float32)
         trans = np.empty((n, 2, 3), np.float32)
         if isinstance(frame_bgr, torch.Tensor):
@@ -273,10 +301,17 @@ class Engine:
         with torch.cuda.device(self.device):
             for lo in range(0, n, self.max_batch):
                 hi = min(n, lo + self.max_batch)
-                self.check(self.lib.hm_preprocess_centers(
-                    self.h, C.c_void_p(fptr), H, W, stride, on_dev, C.c_void_p(ccs[lo:hi].ctypes.data),
-                    C.c_void_p(md[lo:hi].ctypes.data), hi - lo, _ptr(img[lo:hi]), C.c_void_p(trans[lo:hi].ctypes.data),
-                    self.stream()))
+                if radius is None:
+                    self.check(self.lib.hm_preprocess_centers(
+                        self.h, C.c_void_p(fptr), H, W, stride, on_dev, C.c_void_p(ccs[lo:hi].ctypes.data),
+                        C.c_void_p(md[lo:hi].ctypes.data), hi - lo, _ptr(img[lo:hi]), C.c_void_p(trans[lo:hi].ctypes.data),
+                        self.stream()))
+                else:
+                    self.check(self.lib.hm_preprocess_blur(
+                        self.h, C.c_void_p(fptr), H, W, stride, on_dev, C.c_void_p(ccs[lo:hi].ctypes.data),
+                        C.c_void_p(md[lo:hi].ctypes.data), C.c_void_p(radius[lo:hi].ctypes.data),
+                        C.c_void_p(weights[lo:hi].ctypes.data), hi - lo, _ptr(img[lo:hi]), C.c_void_p(trans[lo:hi].ctypes.data),
+                        self.stream()))
         return img, trans
 
     def camera_postprocess(self, pred_cam, kp3d, meta, fxfy_differ, add_center):

@@ -146,6 +146,18 @@ int hm_mano_lbs(hm_ctx* ctx, const float* betas, const float* rotmats, const flo
 int hm_camera_postprocess(hm_ctx* ctx, const float* pred_cam, float* kp3d, const float* meta, int meta_stride,
                           int fxfy_differ, int add_center, int n, float* cam_t_full, float* kp2d_full, void* stream);
 
+/* hm_preprocess_blur: hm_preprocess_centers with the anti-alias pre-blur of ViTDetDataset.__getitem__
+ * (hamer/hamer/datasets/vitdet_dataset.py:62-71) and prepare_item (hamer/infer.py:312-316): when the crop window is more
+ * than 2.2 x the patch the reference blurs the frame with skimage.filters.gaussian(sigma = (bbox_size / 256 / 2 - 1) / 2)
+ * (= scipy.ndimage.gaussian_filter, mode 'nearest', truncate 4) and warps the float64 result.
+ *   blur_radius : HOST [n] int32, int(4 sigma + 0.5) in [0, 32]; 0 = no blur (the crop is the 8-bit one of hm_preprocess)
+ *   blur_weights: HOST [n, 33] float64, [i, k] = normalised gaussian weight at offset +-k (k <= radius) - computed by the
+ *                 caller with numpy like scipy's _gaussian_kernel1d, so the crop matches the reference bit for bit. */
+#define HM_BLUR_MAX_RADIUS 32
+int hm_preprocess_blur(hm_ctx* ctx, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
+                       const double* center_size, const uint8_t* mode, const int32_t* blur_radius, const double* blur_weights,
+                       int n, float* img_out, float* trans, void* stream);
+
 /* ---- detector hand-off on the device (the YOLOv7 detector itself stays upstream) --------------------------------------
  * hm_letterbox replaces LoadImage.process_img (yolo/yolov7/utils/datasets.py:137-141: letterbox(img0, new_size, stride,
  * auto=True), datasets.py:999-1030 = cv2.resize INTER_LINEAR + cv2.copyMakeBorder 114; BGR -> RGB; HWC -> CHW) and the

@@ -138,6 +138,79 @@ def warp_affine_u8(img, M, out_w=IMAGE_SIZE, out_h=IMAGE_SIZE):
     return ((acc + (1 << 14)) >> 15).astype(np.uint8)
 
 
+def gaussian_kernel1d(sigma, radius):
+    """scipy.ndimage._filters._gaussian_kernel1d (order 0).  sigma keeps the caller's type: ViTDetDataset hands skimage a
+    numpy float32 (float32 boxes, vitdet_dataset.py:37-42), so sigma * sigma and -0.5 / sigma2 round to float32 there."""
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / sigma2 * x ** 2)
+    return phi / phi.sum()
+
+
+def skimage_gaussian(img_u8, sigma, truncate=4.0):
+    """skimage.filters.gaussian(img, sigma=sigma, channel_axis=2, preserve_range=True) for a uint8 HxWx3 image
+    (vitdet_dataset.py:71, infer.py:316).  scikit-image is not installed here; its gaussian() is a thin wrapper:
+    image.astype(float64), then scipy.ndimage.gaussian_filter(image, (sigma, sigma, 0), mode='nearest', cval=0, truncate=4.0).
+    This is the numpy statement of what scipy computes (ni_filters.c NI_Correlate1D with symmetric weights: centre tap first,
+    then (x[-k] + x[+k]) * w_k for k = radius .. 1; rows, then columns) - pinned bit for bit to scipy itself in
+    tests/test_oracle_crop.py."""
+    r = int(truncate * float(sigma) + 0.5)
+    w = gaussian_kernel1d(sigma, r)
+    x = img_u8.astype(np.float64)
+
+    def pass1d(a, axis):
+        n = a.shape[axis]
+        idx = np.arange(n)
+        out = a * w[r]
+        for k in range(r, 0, -1):
+            out = out + (np.take(a, np.clip(idx - k, 0, n - 1), axis=axis) + np.take(a, np.clip(idx + k, 0, n - 1), axis=axis)) * w[r - k]
+        return out
+    return pass1d(pass1d(x, 0), 1)
+
+
+def warp_affine_f64(img, M):
+    """cv2.warpAffine(img float64 HxWxC, M, (256, 256), INTER_LINEAR, BORDER_CONSTANT 0): the same fixed-point coordinates
+    as the 8-bit path (1/32-pixel fractions) but float weights (the products {1 - f/32, f/32} x {1 - g/32, g/32} in float32)
+    and double accumulation S00 w00 + S01 w01 + S10 w10 + S11 w11 (imgproc/imgwarp.cpp remapBilinear<Cast<double, double>, ..., float>).
+    Pinned to cv2 in tests/test_oracle_crop.py."""
+    H, W = img.shape[:2]
+    m = np.array(M, dtype=np.float64).reshape(2, 3).copy()
+    D = m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]                 # cv::warpAffine's own inversion (as in warp_affine_u8)
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = m[1, 1] * D, m[0, 0] * D
+    m[0, 0] = A11
+    m[0, 1] *= -D
+    m[1, 0] *= -D
+    m[1, 1] = A22
+    b1 = -m[0, 0] * m[0, 2] - m[0, 1] * m[1, 2]
+    b2 = -m[1, 0] * m[0, 2] - m[1, 1] * m[1, 2]
+    m[0, 2], m[1, 2] = b1, b2
+    x = np.arange(IMAGE_SIZE)
+    y = np.arange(IMAGE_SIZE)
+    adelta = np.rint(m[0, 0] * x * AB_SCALE).astype(np.int64)
+    bdelta = np.rint(m[1, 0] * x * AB_SCALE).astype(np.int64)
+    rd = AB_SCALE // INTER_TAB // 2
+    X0 = np.rint((m[0, 1] * y + m[0, 2]) * AB_SCALE).astype(np.int64) + rd
+    Y0 = np.rint((m[1, 1] * y + m[1, 2]) * AB_SCALE).astype(np.int64) + rd
+    X = (X0[:, None] + adelta[None, :]) >> (AB_BITS - INTER_BITS)
+    Y = (Y0[:, None] + bdelta[None, :]) >> (AB_BITS - INTER_BITS)
+    sx = np.clip(X >> INTER_BITS, -32768, 32767)
+    sy = np.clip(Y >> INTER_BITS, -32768, 32767)
+    fx = X & (INTER_TAB - 1)
+    fy = Y & (INTER_TAB - 1)
+    f = np.arange(INTER_TAB, dtype=np.float32) * np.float32(1.0 / INTER_TAB)
+    t1 = np.stack([np.float32(1.0) - f, f], 1)
+
+    def tap(yy, xx):
+        inside = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        v = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)]
+        return np.where(inside[..., None], v, 0.0)
+
+    def wgt(a, b):
+        return (t1[fy, a] * t1[fx, b]).astype(np.float64)[..., None]
+    return tap(sy, sx) * wgt(0, 0) + tap(sy, sx + 1) * wgt(0, 1) + tap(sy + 1, sx) * wgt(1, 0) + tap(sy + 1, sx + 1) * wgt(1, 1)
+
+
 def crop_one(img_bgr, label, box):
     """One iteration of the loop in prepare_batch_bbox (infer.py:162-248).
     Returns (img (3,256,256) f32, center (2,), size, trans (2,3) f64, do_flip)."""
@@ -171,7 +244,7 @@ def prepare_batch_bbox(img_bgr, boxes):
 
 
 def vitdet_item(img_bgr, box, right, rescale_factor=2.5):
-    """ViTDetDataset.__getitem__ (hamer/hamer/datasets/vitdet_dataset.py:48-95) for boxes that need no anti-alias blur:
+    """ViTDetDataset.__getitem__ (hamer/hamer/datasets/vitdet_dataset.py:48-95), anti-alias blur included:
     float32 box arithmetic (:37-42, 52-58), flip INSIDE the warp (generate_image_patch_cv2 do_flip,
     datasets/utils.py:347-349: the frame is mirrored and c_x = img_width - c_x - 1), BGR->RGB, CHW float32, normalise.
     Returns (img (3,256,256) f32, box_center (2,) f32, box_size f32)."""
@@ -186,14 +259,19 @@ def vitdet_item(img_bgr, box, right, rescale_factor=2.5):
     else:
         new = np.array([max(h * w_t / h_t, w), h])
     bbox_size = new.max()
-    assert (bbox_size * 1.0) / IMAGE_SIZE / 2.0 <= 1.1, 'anti-aliased item: not restated'
     c_x, c_y = center[0], center[1]
     img = img_bgr
+    downsampling_factor = (bbox_size * 1.0) / IMAGE_SIZE / 2.0
+    if downsampling_factor > 1.1:                       # vitdet_dataset.py:62-71: blur the frame, warp the float64 image
+        img = skimage_gaussian(img, (downsampling_factor - 1) / 2)
     if right == 0:
         img = img[:, ::-1, :]
         c_x = img.shape[1] - c_x - 1
     M = affine_from_box(float(c_x), float(c_y), float(bbox_size))
-    patch = warp_affine_u8(np.ascontiguousarray(img), M)[:, :, ::-1]
+    if img.dtype == np.uint8:
+        patch = warp_affine_u8(np.ascontiguousarray(img), M)[:, :, ::-1]
+    else:
+        patch = warp_affine_f64(np.ascontiguousarray(img), M)[:, :, ::-1]
     t = np.transpose(patch, (2, 0, 1)).astype(np.float32)
     mean = 255.0 * np.array(IMAGE_MEAN)
     std = 255.0 * np.array(IMAGE_STD)

@@ -206,8 +206,18 @@ def test_vitdet_dataset_and_hamer_infer(model, oracle_model):
         assert np.array_equal(item['img'], t) and np.array_equal(b['img'][i].cpu().numpy(), t)
         assert np.array_equal(item['box_center'], center) and item['box_size'] == size and item['right'] == right[i]
         assert item['personid'] == i and np.array_equal(item['img_size'], np.array([640., 480.]))
-    with pytest.raises(NotImplementedError):
-        ViTDetDataset(default_config(), frame, np.array([[0, 0, 600, 400]], np.float32), np.array([1]), engine=model.engine)[0]
+    # crop windows > 563 px: the frame is blurred (skimage gaussian = scipy gaussian_filter) and the float64 image is warped
+    # (vitdet_dataset.py:62-71) - bit-exact as well, both hands, frame borders inside the blur's support
+    big = synthetic_frame(1080, 1920, 32)
+    bboxes = np.array([[500, 200, 900, 640], [1500.5, 600.25, 1915, 1075], [0, 0, 700, 900], [300, 300, 450, 500]], np.float32)
+    bright = np.array([1, 0, 0, 1])
+    dsb = ViTDetDataset(default_config(), big, bboxes, bright, engine=model.engine)
+    bb = dsb.batch()
+    for i in range(4):
+        t, center, size = oc.vitdet_item(big, bboxes[i], bright[i])
+        assert (size / 256 / 2 > 1.1) == (i < 3)                     # the last box takes the 8-bit path inside the same call
+        assert np.array_equal(bb['img'][i].cpu().numpy(), t), i
+        assert dsb[i]['box_size'] == size
     infer = HAMER_INFER.__new__(HAMER_INFER)
     infer.__dict__.update(model.__dict__)                    # same engine / weights, the inference-only surface
     out = infer({'img': b['img'][:2]})

@@ -133,3 +133,34 @@ def test_vitdet_item_against_reference_functions():
         for ch in range(3):
             ref[ch] = (ref[ch] - np.float32(mean[ch])) / np.float32(std[ch])
         assert np.array_equal(t, ref)
+
+
+def test_antialias_blur_and_float_warp_against_scipy_and_cv2():
+    """The anti-aliased item (vitdet_dataset.py:62-71): oracle.crop.skimage_gaussian states what scipy.ndimage.gaussian_filter
+    computes (skimage.filters.gaussian's backend; mode 'nearest', truncate 4) and warp_affine_f64 what cv2.warpAffine does on
+    a float64 image - both bit for bit, so the CUDA path (which evaluates the same formulas) is pinned to the libraries the
+    reference calls."""
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (300, 420, 3), dtype=np.uint8)
+    for sigma in (0.135, 0.28, 0.67, 1.94, 3.3):
+        ref = ndi.gaussian_filter(img.astype(np.float64), sigma=(sigma, sigma, 0), mode='nearest', cval=0, truncate=4.0)
+        assert np.array_equal(oc.skimage_gaussian(img, sigma), ref)
+    big = rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    for cx, cy, size in [(600.0, 300.0, 800.0), (100.0, 100.0, 1200.0), (1200.5, 700.25, 650.3)]:
+        sigma = (size / 256 / 2 - 1) / 2
+        bl = oc.skimage_gaussian(big, sigma)
+        M = oc.affine_from_box(cx, cy, size)
+        ref = cv2.warpAffine(bl, M, (256, 256), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        assert np.array_equal(oc.warp_affine_f64(bl, M), ref)
+    # and a whole anti-aliased ViTDetDataset item, left hand (flip inside the warp)
+    t, center, size = oc.vitdet_item(big, (300, 100, 700, 640), 0)
+    assert size / 256 / 2 > 1.1 and t.shape == (3, 256, 256) and t.dtype == np.float32
+    fr = ndi.gaussian_filter(big.astype(np.float64), sigma=((size / 256 / 2 - 1) / 2,) * 2 + (0,), mode='nearest', truncate=4.0)[:, ::-1, :]
+    M = oc.affine_from_box(float(big.shape[1] - center[0] - 1), float(center[1]), float(size))
+    patch = cv2.warpAffine(np.ascontiguousarray(fr), M, (256, 256), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    ref = np.transpose(patch[:, :, ::-1], (2, 0, 1)).astype(np.float32)
+    mean = 255. * np.array([0.485, 0.456, 0.406]); std = 255. * np.array([0.229, 0.224, 0.225])
+    for ch in range(3):
+        ref[ch] = (ref[ch] - np.float32(mean[ch])) / np.float32(std[ch])
+    assert np.array_equal(t, ref)
