@@ -12,7 +12,7 @@ from .configs import CfgNode, default_config
 from .mano_data import load_mano_pkl, synthetic_mano
 
 __all__ = ['CfgNode', 'default_config', 'load_mano_pkl', 'synthetic_mano', 'HAMER', 'load_hamer',
-           'hamer_inference', 'Engine', 'HAMER_INFER', 'ViTDetDataset']
+           'hamer_inference', 'Engine', 'HAMER_INFER', 'ViTDetDataset', 'RootNet']
 
 
 def __getattr__(name):
@@ -23,6 +23,9 @@ def __getattr__(name):
     if name == 'ViTDetDataset':
         from .datasets import ViTDetDataset
         return ViTDetDataset
+    if name == 'RootNet':
+        from .rootnet import RootNet
+        return RootNet
     if name == 'hamer_inference':
         from .inference import hamer_inference
         return hamer_inference

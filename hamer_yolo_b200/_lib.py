@@ -32,8 +32,8 @@ class HmError(RuntimeError):
 # every symbol include/hamer_b200.h declares (tests check the library exports all of them)
 EXPORTS = ('hm_create', 'hm_destroy', 'hm_last_error', 'hm_set_weight', 'hm_finalize_weights',
            'hm_set_mano', 'hm_preprocess', 'hm_preprocess_centers', 'hm_preprocess_blur', 'hm_forward', 'hm_backbone', 'hm_mano_head',
-           'hm_mano_lbs', 'hm_camera_postprocess', 'hm_rotmat_to_axis_angle', 'hm_letterbox_shape', 'hm_letterbox', 'hm_scale_boxes', 'hm_comm_unique_id', 'hm_comm_init', 'hm_comm_destroy', 'hm_allgather', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
-           'hm_profile_collect', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention', 'hm_test_mano_clocks')
+           'hm_mano_lbs', 'hm_camera_postprocess', 'hm_rotmat_to_axis_angle', 'hm_letterbox_shape', 'hm_letterbox', 'hm_scale_boxes', 'hm_rootnet_finalize', 'hm_rootnet_depth', 'hm_comm_unique_id', 'hm_comm_init', 'hm_comm_destroy', 'hm_allgather', 'hm_forward_launch_count', 'hm_version', 'hm_profile_enable',
+           'hm_profile_collect', 'hm_test_rootnet_patches', 'hm_test_gemm', 'hm_test_layernorm', 'hm_test_attention', 'hm_test_mano_clocks')
 
 PROFILE_CATEGORIES = ('im2col', 'gemm_patch', 'layernorm', 'gemm_qkv', 'attention', 'gemm_proj',
                       'gemm_fc1', 'gemm_fc2', 'head', 'mano_lbs', 'crop')
@@ -71,6 +71,8 @@ def load():
     lib.hm_letterbox_shape.argtypes = [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.hm_letterbox.argtypes = [vp, vp, i32, i32, C.c_int64, i32, i32, i32, i32, vp, C.POINTER(vp), vp]
     lib.hm_scale_boxes.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.hm_rootnet_finalize.argtypes = [vp]
+    lib.hm_rootnet_depth.argtypes = [vp, vp, i32, i32, i64, i32, vp, vp, i32, vp, vp]
     lib.hm_comm_unique_id.argtypes = [vp]
     lib.hm_comm_init.argtypes = [vp, vp, i32, i32]
     lib.hm_comm_destroy.argtypes = [vp]
@@ -80,6 +82,7 @@ def load():
     lib.hm_version.restype = C.c_char_p
     lib.hm_profile_enable.argtypes = [vp, i32]
     lib.hm_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32), i32]
+    lib.hm_test_rootnet_patches.argtypes = [vp, i32, vp, vp]
     lib.hm_test_gemm.argtypes =[vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.hm_test_mano_clocks.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, vp]
     lib.hm_test_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, i32, vp]

@@ -169,6 +169,10 @@ inline cudaError_t gemm_launch_e(int epi, const CUtensorMap& ta, const CUtensorM
         case EPI_BIAS_RESID_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_RESID_F32>(ta, tb, tout, p, num_sms, s);
         case EPI_BIAS_POS_F32: return gemm_launch_t<CTA_GROUP, BN, EPI_BIAS_POS_F32>(ta, tb, tout, p, num_sms, s);
     }
+    if constexpr (CTA_GROUP == 1 && BN == 128) {      // the RootNet convolutions only use single-CTA 128 x 128 tiles
+        if (epi == EPI_BIAS_RELU_F16) return gemm_launch_t<1, 128, EPI_BIAS_RELU_F16>(ta, tb, tout, p, num_sms, s);
+        if (epi == EPI_BIAS_RESID_RELU_F16) return gemm_launch_t<1, 128, EPI_BIAS_RESID_RELU_F16>(ta, tb, tout, p, num_sms, s);
+    }
     return cudaErrorInvalidValue;
 }
 

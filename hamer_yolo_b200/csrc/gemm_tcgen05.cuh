@@ -41,6 +41,8 @@ enum GemmEpilogue : int {
     EPI_BIAS_GELU_BF16 = 1,  // out_f16[m,n] = gelu(acc + bias[n])
     EPI_BIAS_RESID_F32 = 2,  // out_f32[m,n] += acc + bias[n]
     EPI_BIAS_POS_F32 = 3,    // out_f32[m,n]  = acc + bias[n] + pos[(m % pos_rows), n]
+    EPI_BIAS_RELU_F16 = 4,        // out_f16[m,n] = relu(acc + bias[n])                    (RootNet convolutions, BatchNorm folded)
+    EPI_BIAS_RESID_RELU_F16 = 5,  // out_f16[m,n] = relu(acc + bias[n] + resid_f16[m,n])   (BasicBlock tail)
 };
 
 struct GemmParams {
@@ -51,6 +53,7 @@ struct GemmParams {
     int ldo;            // elements
     const float* pos;   // [pos_rows, N] (EPI_BIAS_POS_F32)
     int pos_rows;
+    const void* resid;  // [M, ldo] fp16 (EPI_BIAS_RESID_RELU_F16)
     int ksplit_workers; // worker count the split was planned for (set by gemm_launch)
     int ksplit;         // EPI_BIAS_RESID_F32 only: the tiles of the last, partial wave are split into `ksplit`
                         // K-slices (each slice reduce-adds its partial product; slice 0 carries the bias); <= 1 = off
@@ -324,6 +327,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) v[e] = gelu_erf2(v[e]);
+                            }
+                            if constexpr (EPI == EPI_BIAS_RESID_RELU_F16) {
+                                const uint4 rq = *reinterpret_cast<const uint4*>(
+                                    reinterpret_cast<const __half*>(p.resid) + (size_t)row * p.ldo + col + j * 8);
+                                const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rw[e]));
+                                    v[e] = __fadd2_rn(v[e], rf);
+                                }
+                            }
+                            if constexpr (EPI == EPI_BIAS_RELU_F16 || EPI == EPI_BIAS_RESID_RELU_F16) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) v[e] = make_float2(fmaxf(v[e].x, 0.f), fmaxf(v[e].y, 0.f));
                             }
                             uint4 o;
                             o.x = pack_act2(v[0].x, v[0].y);

@@ -24,6 +24,7 @@
 #include "letterbox.cuh"
 #include "mano_lbs.cuh"
 #include "mano_fused.cuh"
+#include "rootnet.cuh"
 
 using namespace hm;
 
@@ -154,6 +155,14 @@ struct hm_ctx {
     bool crop_kernel_recorded = false;
 
     std::vector<void*> allocs;
+
+    // RootNet / SAR depth (hm_rootnet_*): BatchNorm-folded fp16 convolution weights, workspace for RN_CHUNK hands
+    struct RnConv { int cin, cout, k, stride, pad, kpad, npad, hin, hout; __half* w; float* bias; CUtensorMap tm_w, tm_a; };
+    RnConv rn[RN_NCONV];
+    bool rn_ready = false;
+    std::vector<void*> rn_allocs;
+    float *rn_img = nullptr, *rn_lut = nullptr, *rn_wd = nullptr, *rn_bd = nullptr, *rn_kval = nullptr;
+    __half *rn_col = nullptr, *rn_act[4] = {};
 
     // the context's own NCCL communicator (hm_comm_init), one rank per context / GPU
     ncclComm_t comm = nullptr;
@@ -678,6 +687,7 @@ void hm_destroy(hm_ctx* c) {
     if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
     for (void* p : c->allocs) cudaFree(p);
     for (void* p : c->mano_allocs) cudaFree(p);
+    for (void* p : c->rn_allocs) cudaFree(p);
     for (auto& kv : c->w) { cudaFree(kv.second.f32); cudaFree(kv.second.bf16); }
     if (c->crop_host) cudaFreeHost(c->crop_host);
     if (c->blur_host) cudaFreeHost(c->blur_host);
@@ -696,7 +706,7 @@ int hm_set_weight(hm_ctx* c, const char* name, const float* data, const int64_t*
     const std::string key(name);
     auto old = c->w.find(key);
     if (old != c->w.end()) { cudaFree(old->second.f32); cudaFree(old->second.bf16); c->w.erase(old); }
-    c->finalized = false;
+    if (key.rfind("rootnet.", 0) == 0) c->rn_ready = false; else c->finalized = false;
     HM_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&t.f32), t.numel * 4));
     cudaError_t e = cudaMemcpy(t.f32, data, t.numel * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && is_backbone_matrix(key) && ndim == 2) {
@@ -1019,6 +1029,7 @@ int hm_set_mano(hm_ctx* c, const float* v_template, const float* shapedirs, cons
         for (int q = 0; q < 5; ++q) { c->mano_chain.tip_slot[q] = c->mano.tip_slot[q]; c->mano_chain.tip_ids[q] = tip_ids[q]; }
     }
     for (void* p : c->mano_allocs) cudaFree(p);
+    for (void* p : c->rn_allocs) cudaFree(p);
     c->mano_allocs.clear();
     c->mano_set = false;
     auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
@@ -1510,6 +1521,241 @@ int hm_forward_launch_count(const hm_ctx* ctx) {
     // im2col + patch GEMM + 32 x (LN, qkv, attention, proj, LN, fc1, fc2) + last LN
     // + decoder (token init + 6 x 8 + read-out + finalize) + MANO (one fused kernel; 3 on the three-kernel path)
     return 2 + DEPTH * 7 + 1 + (1 + HDEPTH * 8 + 2) + ((ctx && (ctx->mano_legacy || !ctx->mano_fused_ok)) ? 3 : 1);
+}
+
+// ---- RootNet / SAR root depth ---------------------------------------------------------------------------
+namespace {
+
+// the 36 convolutions of torchvision's ResNet-34 in execution order, with their state-dict prefixes inside SARresnet34
+// (rootnet/Model_RGB.py:179-197: extract_mid = [conv1, bn1, relu, maxpool, layer1, layer2], extract_high[0] = [layer3, layer4])
+struct RnSpec { std::string conv, bn; int cin, cout, k, stride, pad, hin; };
+std::vector<RnSpec> rn_specs() {
+    std::vector<RnSpec> v;
+    v.push_back({"extract_mid.0", "extract_mid.1", 3, 64, 7, 2, 3, 256});
+    const char* layer_prefix[4] = {"extract_mid.4", "extract_mid.5", "extract_high.0.0", "extract_high.0.1"};
+    const int blocks[4] = {3, 4, 6, 3}, width[4] = {64, 128, 256, 512};
+    int cin = 64, h = 64;
+    for (int l = 0; l < 4; ++l)
+        for (int b = 0; b < blocks[l]; ++b) {
+            const std::string p = std::string(layer_prefix[l]) + "." + std::to_string(b);
+            const int stride = (b == 0 && l > 0) ? 2 : 1, cout = width[l];
+            v.push_back({p + ".conv1", p + ".bn1", cin, cout, 3, stride, 1, h});
+            v.push_back({p + ".conv2", p + ".bn2", cout, cout, 3, 1, 1, h / stride});
+            if (stride == 2) v.push_back({p + ".downsample.0", p + ".downsample.1", cin, cout, 1, 2, 0, h});
+            cin = cout;
+            h /= stride;
+        }
+    return v;
+}
+
+cudaError_t rn_alloc_bytes(hm_ctx* c, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) c->rn_allocs.push_back(*p);
+    return e;
+}
+#define rn_alloc(ctx, pp, count) rn_alloc_bytes(ctx, reinterpret_cast<void**>(pp), (size_t)(count) * sizeof(**(pp)))
+
+}  // namespace
+
+int hm_rootnet_finalize(hm_ctx* c) {
+    if (!c) return HM_ERR_INVALID;
+    HM_CUDA(c, cudaSetDevice(c->device));
+    const std::vector<RnSpec> specs = rn_specs();
+    if ((int)specs.size() != RN_NCONV) return fail(c, HM_ERR_INVALID, "hm_rootnet_finalize: internal layer table");
+    auto get = [&](const std::string& n, std::initializer_list<int64_t> shape, std::vector<float>& h) -> int {
+        const DevTensor* t = find(c, "rootnet.backbone." + n);
+        if (!shape_is(t, shape)) return fail(c, HM_ERR_INVALID, "missing or mis-shaped weight: rootnet.backbone." + n);
+        h.resize(t->numel);
+        HM_CUDA(c, cudaMemcpy(h.data(), t->f32, t->numel * 4, cudaMemcpyDeviceToHost));
+        return HM_OK;
+    };
+    for (void* p : c->rn_allocs) cudaFree(p);
+    c->rn_allocs.clear();
+    c->rn_ready = false;
+    // workspace for RN_CHUNK hands: crops, im2col rows (largest: conv1, 16,384 x 192 per hand), four NHWC activation buffers
+    // (largest: the stem output, 16,384 x 128 per hand)
+    HM_CUDA(c, rn_alloc(c, &c->rn_img, (size_t)RN_CHUNK * 3 * 65536));
+    HM_CUDA(c, rn_alloc(c, &c->rn_col, (size_t)RN_CHUNK * 16384 * 192));
+    HM_CUDA(c, cudaMemset(c->rn_col, 0, (size_t)RN_CHUNK * 16384 * 192 * 2));
+    for (int i = 0; i < 4; ++i) {
+        HM_CUDA(c, rn_alloc(c, &c->rn_act[i], (size_t)RN_CHUNK * 16384 * 128));
+        HM_CUDA(c, cudaMemset(c->rn_act[i], 0, (size_t)RN_CHUNK * 16384 * 128 * 2));
+    }
+    HM_CUDA(c, rn_alloc(c, &c->rn_lut, (size_t)768));
+    HM_CUDA(c, rn_alloc(c, &c->rn_wd, (size_t)512));
+    HM_CUDA(c, rn_alloc(c, &c->rn_bd, (size_t)1));
+    HM_CUDA(c, rn_alloc(c, &c->rn_kval, (size_t)RN_CHUNK));
+    {   // ToTensor + Normalize (Model_RGB.py:317-318) as a table: (v / 255 - mean) / std, torchvision's float32 operations
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+        float lut[768];
+        for (int ch = 0; ch < 3; ++ch)
+            for (int v = 0; v < 256; ++v) lut[ch * 256 + v] = ((float)v / 255.0f - mean[ch]) / stdv[ch];
+        HM_CUDA(c, cudaMemcpy(c->rn_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
+    std::vector<float> w, g, b, mu, var;
+    for (int i = 0; i < RN_NCONV; ++i) {
+        const RnSpec& sp = specs[i];
+        hm_ctx::RnConv& cv = c->rn[i];
+        cv.cin = sp.cin; cv.cout = sp.cout; cv.k = sp.k; cv.stride = sp.stride; cv.pad = sp.pad;
+        cv.hin = sp.hin; cv.hout = (sp.hin + 2 * sp.pad - sp.k) / sp.stride + 1;
+        const int K = sp.k * sp.k * sp.cin;
+        cv.kpad = (K + 63) / 64 * 64;
+        cv.npad = (sp.cout + 127) / 128 * 128;
+        int rc;
+        if ((rc = get(sp.conv + ".weight", {sp.cout, sp.cin, sp.k, sp.k}, w)) || (rc = get(sp.bn + ".weight", {sp.cout}, g)) ||
+            (rc = get(sp.bn + ".bias", {sp.cout}, b)) || (rc = get(sp.bn + ".running_mean", {sp.cout}, mu)) ||
+            (rc = get(sp.bn + ".running_var", {sp.cout}, var)))
+            return rc;
+        // BatchNorm2d (eval, eps 1e-5) folded: w' = w gamma / sqrt(var + eps), b' = beta - mean gamma / sqrt(var + eps);
+        // K order (ky, kx, c) to match the NHWC im2col; fp16 operands, padded rows / columns are zero
+        std::vector<uint16_t> w16((size_t)cv.npad * cv.kpad, 0);
+        std::vector<float> bias(cv.npad, 0.f);
+        for (int o = 0; o < sp.cout; ++o) {
+            const double sc = (double)g[o] / sqrt((double)var[o] + 1e-5);
+            bias[o] = (float)((double)b[o] - (double)mu[o] * sc);
+            for (int ci = 0; ci < sp.cin; ++ci)
+                for (int ky = 0; ky < sp.k; ++ky)
+                    for (int kx = 0; kx < sp.k; ++kx) {
+                        const float v = (float)((double)w[(((size_t)o * sp.cin + ci) * sp.k + ky) * sp.k + kx] * sc);
+                        const __half hv = __float2half_rn(v);
+                        w16[(size_t)o * cv.kpad + (size_t)(ky * sp.k + kx) * sp.cin + ci] = *reinterpret_cast<const uint16_t*>(&hv);
+                    }
+        }
+        HM_CUDA(c, rn_alloc(c, &cv.w, w16.size()));
+        HM_CUDA(c, rn_alloc(c, &cv.bias, bias.size()));
+        HM_CUDA(c, cudaMemcpy(cv.w, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+        HM_CUDA(c, cudaMemcpy(cv.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+        const uint64_t rows = (uint64_t)RN_CHUNK * cv.hout * cv.hout;
+        if (!make_tmap_bf16_2d(&cv.tm_w, cv.w, cv.npad, cv.kpad, cv.kpad, 128) ||
+            !make_tmap_bf16_2d(&cv.tm_a, c->rn_col, rows, cv.kpad, cv.kpad, GEMM_BM))
+            return fail(c, HM_ERR_CUDA, "hm_rootnet_finalize: tensor-map encoding failed");
+    }
+    {   // ResRootNet.depth_layer (Model_RGB.py:256-262): Conv2d(512, 1, 1)
+        const DevTensor* wd = find(c, "rootnet.rootnet.depth_layer.weight");
+        const DevTensor* bd = find(c, "rootnet.rootnet.depth_layer.bias");
+        if (!shape_is(wd, {1, 512, 1, 1}) || !shape_is(bd, {1})) return fail(c, HM_ERR_INVALID, "missing or mis-shaped weight: rootnet.rootnet.depth_layer");
+        HM_CUDA(c, cudaMemcpy(c->rn_wd, wd->f32, 512 * 4, cudaMemcpyDeviceToDevice));
+        HM_CUDA(c, cudaMemcpy(c->rn_bd, bd->f32, 4, cudaMemcpyDeviceToDevice));
+    }
+    c->rn_ready = true;
+    return HM_OK;
+}
+
+namespace {
+
+// one convolution of the chunk: im2col of `in` (NHWC, pitch ld_in) into the shared column buffer, then the GEMM
+int rn_conv(hm_ctx* c, int idx, const __half* in, int ld_in, int n, int epi, __half* out, const __half* resid, cudaStream_t s) {
+    const hm_ctx::RnConv& cv = c->rn[idx];
+    const int M = n * cv.hout * cv.hout;
+    launch_pdl(rn_im2col_kernel, dim3((M + 7) / 8), dim3(256), 0, s, in, c->rn_col, n, cv.hin, cv.hin, ld_in, cv.cin, cv.k, cv.stride,
+               cv.pad, cv.hout, cv.hout);
+    GemmParams p{};
+    p.M = M; p.N = cv.npad; p.K = cv.kpad; p.bias = cv.bias; p.out = out; p.ldo = cv.npad; p.resid = resid;
+    p.b_format = 0; p.ksplit = -1;
+    HM_CUDA(c, gemm_launch(GemmPlan{1, 128}, epi, cv.tm_a, cv.tm_w, cv.tm_a, p, c->num_sms, s));
+    return HM_OK;
+}
+
+}  // namespace
+
+int hm_rootnet_depth(hm_ctx* c, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
+                     const float* bbox_xywh, const float* k_value, int n, float* depth, void* stream) {
+    if (!c) return HM_ERR_INVALID;
+    if (!c->rn_ready) return fail(c, HM_ERR_STATE, "hm_rootnet_depth: call hm_rootnet_finalize after setting the rootnet.* weights");
+    if (!frame_bgr || !bbox_xywh || !k_value || !depth || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3 || n <= 0)
+        return fail(c, HM_ERR_INVALID, "hm_rootnet_depth: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    HM_CUDA(c, cudaSetDevice(c->device));
+    const uint8_t* frame = frame_bgr;
+    if (!frame_on_device) {
+        const size_t bytes = (size_t)(H - 1) * (size_t)row_stride + (size_t)W * 3;
+        if (!c->frame_dev || bytes > (size_t)c->cfg.max_frame_bytes)
+            return fail(c, HM_ERR_INVALID, "hm_rootnet_depth: frame larger than hm_config.max_frame_bytes");
+        if (c->crop_kernel_recorded) HM_CUDA(c, cudaStreamWaitEvent(s, c->crop_kernel_event, 0));
+        HM_CUDA(c, cudaMemcpyAsync(c->frame_dev, frame_bgr, bytes, cudaMemcpyHostToDevice, s));
+        frame = c->frame_dev;
+    }
+    int rc;
+    for (int lo = 0; lo < n; lo += RN_CHUNK) {
+        const int m = std::min(RN_CHUNK, n - lo);
+        if (m > c->cfg.max_batch) return fail(c, HM_ERR_INVALID, "hm_rootnet_depth: max_batch too small");
+        if (c->crop_event_pending) {          // the pinned crop staging is shared with hm_preprocess
+            HM_CUDA(c, cudaEventSynchronize(c->crop_event));
+            c->crop_event_pending = false;
+        }
+        for (int i = 0; i < m; ++i) {
+            // generate_patch_image (rootnet/preprocessing.py:62-73): float32 source points, LU solve in double, the matrix cast
+            // to float32 before cv2.warpAffine inverts it in double
+            const float* bb = bbox_xywh + 4 * (lo + i);
+            const float cx = bb[0] + 0.5f * bb[2], cy = bb[1] + 0.5f * bb[3];      // numpy float32 arithmetic
+            const float hw = (float)((double)bb[2] * 0.5), hh = (float)((double)bb[3] * 0.5);
+            if (!(bb[2] > 0.f) || !(bb[3] > 0.f)) return fail(c, HM_ERR_INVALID, "hm_rootnet_depth: empty box");
+            const double sx[3] = {cx, cx, (double)(cx + hw)}, sy[3] = {cy, (double)(cy + hh), cy};
+            const double dx[3] = {128, 128, 256}, dy[3] = {128, 256, 128};
+            double A[6][6] = {}, bv[6];
+            for (int q = 0; q < 3; ++q) {
+                A[2 * q][0] = sx[q]; A[2 * q][1] = sy[q]; A[2 * q][2] = 1;
+                A[2 * q + 1][3] = sx[q]; A[2 * q + 1][4] = sy[q]; A[2 * q + 1][5] = 1;
+                bv[2 * q] = dx[q]; bv[2 * q + 1] = dy[q];
+            }
+            lu_solve6(A, bv);
+            double M32[6];
+            for (int q = 0; q < 6; ++q) M32[q] = (double)(float)bv[q];
+            invert_affine(M32, c->crop_host[i].m);
+            c->crop_host[i].flip = 0;
+            c->crop_host[i].pad = 0;
+        }
+        HM_CUDA(c, cudaMemcpyAsync(c->crop_dev, c->crop_host, (size_t)m * sizeof(CropParams), cudaMemcpyHostToDevice, s));
+        HM_CUDA(c, cudaMemcpyAsync(c->rn_kval, k_value + lo, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+        HM_CUDA(c, cudaEventRecord(c->crop_event, s));
+        c->crop_event_pending = true;
+        launch_pdl(crop_warp_normalize_kernel, dim3(256, m), dim3(256), 0, s, frame, H, W, row_stride, (const CropParams*)c->crop_dev,
+                   (const float*)c->rn_lut, c->rn_img);
+        // stem: conv1 + bn1 + relu, maxpool
+        launch_pdl(rn_im2col_conv1_kernel, dim3(128, m), dim3(128), 0, s, (const float*)c->rn_img, c->rn_col);
+        {
+            const hm_ctx::RnConv& cv = c->rn[0];
+            GemmParams p{};
+            p.M = m * 16384; p.N = cv.npad; p.K = cv.kpad; p.bias = cv.bias; p.out = c->rn_act[0]; p.ldo = cv.npad; p.ksplit = -1;
+            HM_CUDA(c, gemm_launch(GemmPlan{1, 128}, EPI_BIAS_RELU_F16, cv.tm_a, cv.tm_w, cv.tm_a, p, c->num_sms, s));
+        }
+        {
+            const size_t total = (size_t)m * 64 * 64 * (128 / 8);
+            launch_pdl(rn_maxpool_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, (const __half*)c->rn_act[0], c->rn_act[1], m, 128, 128, 128);
+        }
+        // BasicBlocks: x -> relu(bn1(conv1 x)) -> bn2(conv2 .) + identity -> relu; identity = x or bn(conv1x1 stride 2 (x))
+        __half *x = c->rn_act[1], *t = c->rn_act[2], *y = c->rn_act[3], *ds = c->rn_act[0];
+        int ld = 128, idx = 1;
+        const int blocks[4] = {3, 4, 6, 3};
+        for (int l = 0; l < 4; ++l)
+            for (int b = 0; b < blocks[l]; ++b) {
+                const bool down = b == 0 && l > 0;
+                const int ld_out = c->rn[idx].npad;
+                if ((rc = rn_conv(c, idx, x, ld, m, EPI_BIAS_RELU_F16, t, nullptr, s))) return rc;
+                const __half* identity = x;
+                if (down) {
+                    if ((rc = rn_conv(c, idx + 2, x, ld, m, EPI_BIAS_BF16, ds, nullptr, s))) return rc;
+                    identity = ds;
+                }
+                if ((rc = rn_conv(c, idx + 1, t, ld_out, m, EPI_BIAS_RESID_RELU_F16, y, identity, s))) return rc;
+                std::swap(x, y);
+                ld = ld_out;
+                idx += down ? 3 : 2;
+            }
+        launch_pdl(rn_head_kernel, dim3(m), dim3(512), 0, s, (const __half*)x, (const float*)c->rn_wd, (const float*)c->rn_bd,
+                   (const float*)c->rn_kval, depth + lo);
+        HM_CUDA(c, cudaGetLastError());
+        HM_CUDA(c, cudaEventRecord(c->crop_kernel_event, s));
+        c->crop_kernel_recorded = true;
+    }
+    return HM_OK;
+}
+
+// test hook: the normalised 256 x 256 patches of the last hm_rootnet_depth chunk (DEVICE out [n,3,256,256], n <= 8)
+int hm_test_rootnet_patches(hm_ctx* c, int n, float* out, void* stream) {
+    if (!c || !c->rn_ready || !out || n <= 0 || n > RN_CHUNK) return fail(c, HM_ERR_INVALID, "hm_test_rootnet_patches: bad arguments");
+    HM_CUDA(c, cudaMemcpyAsync(out, c->rn_img, (size_t)n * 3 * 65536 * 4, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    return HM_OK;
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------

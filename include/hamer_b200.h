@@ -185,6 +185,23 @@ int hm_scale_boxes(hm_ctx* ctx, const void* det, int det_half, int n, int det_st
  * construction). */
 int hm_rotmat_to_axis_angle(hm_ctx* ctx, const float* rotmats, int n, float* axis_angle, void* stream);
 
+/* ---- RootNet / SAR root depth --------------------------------------------------------------------------------------
+ * replaces EstimateRGB.estimate_root_depth_custom (rootnet/Model_RGB.py:572-638), which hamer/infer.py:1275 calls per hand
+ * right after estimate_from_rgb: 256 x 256 crop of the process_bbox'ed window (rootnet/preprocessing.py:39-79, :167-188),
+ * ToTensor + Normalize, SARresnet34 (torchvision ResNet-34 trunk, Model_RGB.py:179-197), ResRootNet (global average pool,
+ * 1 x 1 conv, Model_RGB.py:240-287), depth = gamma * k_value.
+ * Weights: hm_set_weight with the reference's state-dict keys under the prefix "rootnet.": "rootnet.backbone.<key>" for the
+ * entries of checkpoint['model'] that start with "backbone." (convolution weights and the BatchNorm weight / bias /
+ * running_mean / running_var) and "rootnet.rootnet.depth_layer.{weight,bias}" for checkpoint['rootnet'].
+ * hm_rootnet_finalize folds the BatchNorms into fp16 convolution operands (tensor cores, fp32 accumulation) and sizes the
+ * workspace; call it once after the last rootnet.* weight.
+ *   bbox_xywh : HOST [n,4] float32, the PROCESSED boxes (process_bbox(bbox, W, H, (256, 256), 1.5): square windows)
+ *   k_value   : HOST [n] float32, calculate_k (Model_RGB.py:494-498) = sqrt(0.3 * 0.3 * fx * fy / (w * h))
+ *   depth     : DEVICE [n] float32 */
+int hm_rootnet_finalize(hm_ctx* ctx);
+int hm_rootnet_depth(hm_ctx* ctx, const uint8_t* frame_bgr, int H, int W, int64_t row_stride, int frame_on_device,
+                     const float* bbox_xywh, const float* k_value, int n, float* depth, void* stream);
+
 /* ---- multi-GPU --------------------------------------------------------------------------------
  * The reference runs one process and one hand at a time (hamer/infer.py:1268-1274); crops are independent, so the path
  * shards data-parallel: one context per rank / GPU, each rank runs hm_forward on its crops, and ONE collective gathers the
@@ -224,6 +241,7 @@ int hm_profile_collect(hm_ctx* ctx, double* ms_per_cat, int32_t* spans_per_cat, 
  * 2 bias + residual add into f32 out, 3 bias + pos[(m % 192), n] -> f32).  A: DEVICE fp16 bits,
  * W: DEVICE fp16 bits (w_format 0; 1 = both operands bf16), bias/pos: DEVICE f32,
  * out: DEVICE fp16 (epi 0,1) or f32 (epi 2,3). */
+int hm_test_rootnet_patches(hm_ctx* ctx, int n, float* out, void* stream);   /* crops of the last hm_rootnet_depth chunk */
 int hm_test_gemm(hm_ctx* ctx, int cta_group, int bn, int epi, int w_format, const uint16_t* A,
                  const uint16_t* W, const float* bias, const float* pos, void* out, int M, int N,
                  int K, void* stream);
