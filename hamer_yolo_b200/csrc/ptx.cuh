@@ -208,6 +208,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1)
         : "memory");
 }
+// 1-D bulk copy shared -> global (size and both addresses multiples of 16 B), bulk-group completion of the issuing THREAD
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
