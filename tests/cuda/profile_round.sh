@@ -16,7 +16,7 @@ python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_o
 echo "bench rc=$?"; tail -c 3200 gpurun_out/${TAG}_bench.json
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --no-graphs"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$MINE" -s 1248 -c 320 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$MINE" -s 1100 -c 640 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
 if [ -n "$FULL" ]; then

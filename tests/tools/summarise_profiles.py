@@ -19,6 +19,10 @@ def launches():
     hi = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi, gi, bi = (hdr.index(k) for k in ('Kernel Name', 'Metric Value', 'Grid Size', 'Block Size'))
+    # one complete forward = from one im2col launch up to (not including) the next one
+    marks = [i for i, r in enumerate(data) if len(r) > ki and 'im2col_patch16' in r[ki]]
+    if len(marks) >= 2:
+        data = data[marks[-2]:marks[-1]]
     agg = collections.OrderedDict()
     for r in data:
         if len(r) <= vi:
@@ -30,8 +34,8 @@ def launches():
     tot = sum(a[1] for a in agg.values())
     out = ['kernel,grid,block,launches,total_us,avg_us,share']
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        out.append(f'{k[0]},"{k[1]}","{k[2]}",{n},{t / 1000:.1f},{t / 1000 / n:.2f},{t / tot:.3f}')
-    out.append(f'# total {tot / 1000:.1f} us over {len(data)} launches (one bench step, eager launches, ncu serialised / cold cache)')
+        out.append(f'"{k[0]}","{k[1]}","{k[2]}",{n},{t / 1000:.1f},{t / 1000 / n:.2f},{t / tot:.3f}')
+    out.append(f'# total {tot / 1000:.1f} us over {len(data)} launches (one hm_forward of the bench step, eager launches, ncu serialised / cold cache)')
     open(f'{P}/{tag}_launches_summary.csv', 'w').write('\n'.join(out) + '\n')
     print('\n'.join(out))
 
@@ -40,7 +44,13 @@ WANT = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'lts__t_sector_hit_rate.pct',
-        'smsp__inst_executed.sum']
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'lts__t_sectors.avg.pct_of_peak_sustained_elapsed']
 
 
 def full(rep):
@@ -55,7 +65,8 @@ def full(rep):
     seen, out = set(), []
     for r in rows[2:]:
         name = re.sub(r'\(.*', '', re.sub(r'^void ', '', r[hdr.index('Kernel Name')]))
-        key = (name, r[hdr.index('launch__grid_size')])
+        # one entry per distinct launch shape and duration class (proj and fc2 share a kernel and a grid)
+        key = (name, r[hdr.index('launch__grid_size')], round(float(r[hdr.index('gpu__time_duration.sum')].replace(',', '')) / 20.0))
         if key in seen:
             continue
         seen.add(key)
@@ -70,6 +81,7 @@ def full(rep):
         print(json.dumps(d)[:400])
 
 
-launches()
-full('gemm')
-full('misc')
+if os.path.exists(f'{G}/{tag}_launches.csv'):
+    launches()
+for rep in ('gemm', 'misc', 'head', 'mano', 'crop'):
+    full(rep)
