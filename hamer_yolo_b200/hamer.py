@@ -158,21 +158,28 @@ class Engine:
                ('pred_cam_t', (3,)), ('focal_length', (2,)), ('pred_keypoints_3d', (21, 3)),
                ('pred_vertices', (778, 3)), ('pred_keypoints_2d', (21, 2)))
 
+    @classmethod
+    def _flat_floats(cls, B):
+        """Size of the packed output buffer of a graph: every field starts on a 64-byte boundary."""
+        return sum((B * int(np.prod(shp)) + 15) // 16 * 16 for _, shp in cls._FIELDS)
+
     def _views(self, flat, B):
+        # every field starts 64-byte aligned whatever B is: hm_mano_lbs takes its fused kernel only for an 8-byte aligned
+        # vertex pointer, and with tightly packed fields an odd batch put pred_vertices 4 bytes off (the three-kernel
+        # path was taken for 1, 3, 5, ... hands: same tolerances, different bits, slower)
         t, off = {}, 0
         for name, shp in self._FIELDS:
             n = B * int(np.prod(shp))
             t[name] = flat[off:off + n].view(B, *shp)
-            off += n
+            off += (n + 15) // 16 * 16
         return t
 
     def _forward_graph(self, img):
         B = img.shape[0]
         g = self._graphs.pop(B, None)
         if g is None:
-            per = sum(int(np.prod(shp)) for _, shp in self._FIELDS)
             static_img = torch.empty(B, 3, IMG, IMG, device=self.device, dtype=torch.float32)
-            static_flat = torch.empty(B * per, device=self.device, dtype=torch.float32)
+            static_flat = torch.empty(self._flat_floats(B), device=self.device, dtype=torch.float32)
             outs = self._views(static_flat, B)
             s = self._struct(outs, 0, B)
             static_img.copy_(img)
