@@ -40,8 +40,6 @@
 //                private shared-memory tile (row pitch + 16 B: the thread-per-row STS.128 are conflict free) and
 //                stores 8 bytes per lane with the lanes running along the hand's row.
 #pragma once
-#include <type_traits>
-
 #include "mano_lbs.cuh"
 #include "ptx.cuh"
 
@@ -622,32 +620,9 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const __grid_con
                     }
                 const int nu = (!active || (a.dbg & 2)) ? 0 : (int)ptx::lds32(tab);
                 const uint32_t tipmask = active ? ptx::lds32(tab + 4) : 0u;
-                // One union slot = one joint of the group: its transform (tensor memory, per hand) applied to the vertex pairs that
-                // carry a weight for it.  The pair mask is the same for the whole warp; it is broadcast through a shuffle so that
-                // the compiler KNOWS it is uniform and dispatches with one jump into straight-line code per mask value instead of
-                // four branch diamonds with convergence barriers (36 of the loop's 68 instructions per slot were overhead).
-                auto apply_pairs = [&](auto mask_c, const float4 (&Rc)[3], const float2 (&w2)[MF_NP]) {
-                    constexpr uint32_t MASK = decltype(mask_c)::value;
-                    auto pair = [&](auto i_c) {
-                        constexpr int i = decltype(i_c)::value;
-                        if constexpr (i < MF_NP && ((MASK >> i) & 1u) != 0) {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                float2 t = __ffma2_rn(make_float2(Rc[c].z, Rc[c].z), P[i][2], make_float2(Rc[c].w, Rc[c].w));
-                                t = __ffma2_rn(make_float2(Rc[c].y, Rc[c].y), P[i][1], t);
-                                t = __ffma2_rn(make_float2(Rc[c].x, Rc[c].x), P[i][0], t);
-                                O[i][c] = __ffma2_rn(w2[i], t, O[i][c]);
-                            }
-                        }
-                    };
-                    pair(std::integral_constant<int, 0>{});
-                    pair(std::integral_constant<int, 1>{});
-                    pair(std::integral_constant<int, 2>{});
-                    pair(std::integral_constant<int, 3>{});
-                };
                 for (int u = 0; u < nu; ++u) {
-                    const uint32_t jp = __shfl_sync(0xffffffffu, ptx::lds32(tab + 16 + u * 4), 0);
-                    const uint32_t pm = (jp >> 16) & ((1u << MF_NP) - 1u); // vertex pairs with a non-zero weight
+                    const uint32_t jp = ptx::lds32(tab + 16 + u * 4);
+                    const uint32_t pm = jp >> 16;                           // vertex pairs with a non-zero weight
                     uint32_t ta[8], tc[4];
                     ptx::tmem_ld_32x8(tmem_lane + MF_AU_COL + (jp & 0xffffu), ta);
                     ptx::tmem_ld_32x4(tmem_lane + MF_AU_COL + (jp & 0xffffu) + 8, tc);
@@ -663,25 +638,15 @@ mano_fused_kernel(const __grid_constant__ CUtensorMap tm_basis, const __grid_con
                         make_float4(__uint_as_float(ta[0]), __uint_as_float(ta[1]), __uint_as_float(ta[2]), __uint_as_float(ta[3])),
                         make_float4(__uint_as_float(ta[4]), __uint_as_float(ta[5]), __uint_as_float(ta[6]), __uint_as_float(ta[7])),
                         make_float4(__uint_as_float(tc[0]), __uint_as_float(tc[1]), __uint_as_float(tc[2]), __uint_as_float(tc[3]))};
-                    if constexpr (MF_NP == 4) {
-                        switch (pm) {
-#define HM_MF_CASE(m) case m: apply_pairs(std::integral_constant<uint32_t, m>{}, Rc, w2); break;
-                            HM_MF_CASE(1) HM_MF_CASE(2) HM_MF_CASE(3) HM_MF_CASE(4) HM_MF_CASE(5) HM_MF_CASE(6) HM_MF_CASE(7) HM_MF_CASE(8)
-                            HM_MF_CASE(9) HM_MF_CASE(10) HM_MF_CASE(11) HM_MF_CASE(12) HM_MF_CASE(13) HM_MF_CASE(14) HM_MF_CASE(15)
-#undef HM_MF_CASE
-                            default: break;
-                        }
-                    } else {
 #pragma unroll
-                        for (int i = 0; i < MF_NP; ++i) {
-                            if (pm & (1u << i)) {
+                    for (int i = 0; i < MF_NP; ++i) {
+                        if (pm & (1u << i)) {                               // warp-uniform: the weights do not depend on the hand
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    float2 t = __ffma2_rn(make_float2(Rc[c].z, Rc[c].z), P[i][2], make_float2(Rc[c].w, Rc[c].w));
-                                    t = __ffma2_rn(make_float2(Rc[c].y, Rc[c].y), P[i][1], t);
-                                    t = __ffma2_rn(make_float2(Rc[c].x, Rc[c].x), P[i][0], t);
-                                    O[i][c] = __ffma2_rn(w2[i], t, O[i][c]);
-                                }
+                            for (int c = 0; c < 3; ++c) {
+                                float2 t = __ffma2_rn(make_float2(Rc[c].z, Rc[c].z), P[i][2], make_float2(Rc[c].w, Rc[c].w));
+                                t = __ffma2_rn(make_float2(Rc[c].y, Rc[c].y), P[i][1], t);
+                                t = __ffma2_rn(make_float2(Rc[c].x, Rc[c].x), P[i][0], t);
+                                O[i][c] = __ffma2_rn(w2[i], t, O[i][c]);
                             }
                         }
                     }
