@@ -79,12 +79,24 @@ inline bool make_tmap_attn(CUtensorMap* t128, CUtensorMap* t32, const void* base
 
 // Kernel launch, optionally with the programmatic-stream-serialization attribute (PDL): the launch and set-up of
 // kernel n + 1 then overlap the tail of kernel n (every kernel waits on griddepcontrol.wait before touching
-// dependent memory).  Measured inside the replayed CUDA graph: 1-2.5 % at 1-8 crops, nothing at 64
-// (profiles/r01_notes.md), so it is opt-in: HM_PDL=1.
-inline bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("HM_PDL"); return e && e[0] == '1'; }();
-    return on;
+// dependent memory).  Measured inside the replayed CUDA graph (profiles/r02_notes.md): -3 to -5 % at 2-8 crops (a forward
+// is ~280 short kernels there), nothing at 64 crops.  HM_PDL=1 / 0 forces it on / off; unset = automatic: on for calls
+// of at most HM_PDL_MAX_B crops (default 24: -1.8 % there, neutral from 32 on), which the entry points announce through PdlScope.
+inline int pdl_mode() {
+    static const int m = [] { const char* e = getenv("HM_PDL"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+    return m;
 }
+inline int pdl_max_batch() {
+    static const int b = [] { const char* e = getenv("HM_PDL_MAX_B"); return e ? atoi(e) : 24; }();
+    return b;
+}
+inline bool& pdl_auto_flag() { static thread_local bool f = false; return f; }
+inline bool pdl_enabled() { const int m = pdl_mode(); return m == 1 || (m < 0 && pdl_auto_flag()); }
+struct PdlScope {      // marks the launches of one API call as small-batch (automatic PDL)
+    bool prev;
+    explicit PdlScope(int batch) : prev(pdl_auto_flag()) { pdl_auto_flag() = batch <= pdl_max_batch(); }
+    ~PdlScope() { pdl_auto_flag() = prev; }
+};
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

@@ -1429,6 +1429,7 @@ int hm_backbone(hm_ctx* c, const float* img, int B, float* feats, void* stream) 
     if (rc) return rc;
     if (!img || !feats) return fail(c, HM_ERR_INVALID, "hm_backbone: null pointer");
     HM_CUDA(c, cudaSetDevice(c->device));
+    PdlScope pdl(B);
     return backbone_impl(c, img, B, feats, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1437,6 +1438,7 @@ int hm_mano_head(hm_ctx* c, const float* feats, int B, const hm_outputs* out, vo
     if (rc) return rc;
     if (!feats || !out) return fail(c, HM_ERR_INVALID, "hm_mano_head: null pointer");
     HM_CUDA(c, cudaSetDevice(c->device));
+    PdlScope pdl(B);
     return head_impl(c, feats, B, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1458,6 +1460,7 @@ int hm_forward(hm_ctx* c, const float* img, int B, const hm_outputs* out, void* 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     HM_CUDA(c, cudaSetDevice(c->device));
     float* feats = out->conditioning_feats ? out->conditioning_feats : c->feats;
+    PdlScope pdl(B);
     if ((rc = backbone_impl(c, img, B, feats, s))) return rc;
     if ((rc = head_impl(c, feats, B, out, s))) return rc;
     return lbs_impl(c, c->hbetas, c->hrot, c->hcamt, B, out->pred_vertices, out->pred_keypoints_3d,

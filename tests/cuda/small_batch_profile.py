@@ -7,7 +7,7 @@ from hamer_yolo_b200 import load_hamer, synthetic_mano
 from hamer_yolo_b200.weights import random_state_dict
 
 dev = torch.device('cuda:0')
-model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0), device='cuda:0', max_batch=16)
+model, _ = load_hamer(state_dict=random_state_dict(seed=0, device=dev), mano=synthetic_mano(0), device="cuda:0", max_batch=max([int(a) for a in sys.argv[1:]] or [16]))
 eng = model.engine
 for B in [int(a) for a in sys.argv[1:]] or [2, 5, 8]:
     img = torch.randn(B, 3, 256, 256, device=dev)

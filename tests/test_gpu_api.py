@@ -166,9 +166,10 @@ def test_camera_postprocess_kernel_matches_torch_bitwise(model, use_k):
     assert torch.equal(t, t_ref) and torch.equal(uv, uv_ref) and torch.equal(kp_d, kp_ref)
 
 
-def test_opt_in_programmatic_dependent_launch(tmp_path):
-    """HM_PDL=1 (launches carry the programmatic-stream-serialization attribute; every kernel waits on
-    griddepcontrol.wait): same results as the default launches, eager and graph-replayed."""
+def test_programmatic_dependent_launch_changes_no_bits(tmp_path):
+    """Programmatic dependent launch (the launches carry the programmatic-stream-serialization attribute; every kernel waits
+    on griddepcontrol.wait) is automatic for small batches; HM_PDL=0 / 1 force it off / on: identical results, eager and
+    graph-replayed."""
     import os
     import subprocess
     import sys
