@@ -50,7 +50,7 @@ constexpr int SK_WARPS = 8;
 constexpr int SK_KMAX = 1280;   // largest K (cross-attention value projection)
 constexpr int SK_SMEM_MAX = 200 * 1024;
 // X tile + the lane-private W slots (8 warps x CPW columns x K floats)
-__host__ __device__ constexpr size_t sk_smem_bytes(int K, int cpw) { return (size_t)(SK_ROWS + SK_WARPS * cpw) * K * sizeof(float); }
+__host__ __device__ constexpr size_t sk_smem_bytes(int K, int cpw) { return (size_t)(SK_ROWS + SK_WARPS * cpw + 2) * K * sizeof(float); }   // + LayerNorm gamma / beta
 
 __device__ __forceinline__ void sk_cp_async16(float* smem_dst, const float* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
@@ -111,6 +111,11 @@ skinny_linear_kernel(const SkinnyParams p) {
         if (r < rows) sk_cp_async16(dst, X + (size_t)(b0 + r) * p.ldx + c * 4);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // no predicates in the inner loop
     }
+    float* sk_ln = sk_smem + (size_t)(SK_ROWS + SK_WARPS * CPW) * K;   // LNF: [gamma (K) | beta (K)], behind the W slots
+    if constexpr (LNF) {                                        // the LayerNorm parameters ride with the X tile (same copy group):
+        for (int e = threadIdx.x; e < 2 * K4; e += blockDim.x)  // read from global inside the normalisation they were an exposed L2 trip
+            sk_cp_async16(sk_ln + e * 4, (e < K4 ? p.ln_g : p.ln_b - K) + e * 4);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
     const float* wrow[CPW];                                     // columns past N re-read the last valid row (results dropped)
 #pragma unroll
@@ -131,8 +136,8 @@ skinny_linear_kernel(const SkinnyParams p) {
     __syncthreads();
     if constexpr (LNF) {
         // PreNorm: rows 2 warp, 2 warp + 1 of the staged tile, two-pass statistics (same arithmetic as layernorm_kernel)
-        const float4* g4 = reinterpret_cast<const float4*>(p.ln_g);
-        const float4* b4 = reinterpret_cast<const float4*>(p.ln_b);
+        const float4* g4 = reinterpret_cast<const float4*>(sk_ln);
+        const float4* b4 = reinterpret_cast<const float4*>(sk_ln + K);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             float4* xr = reinterpret_cast<float4*>(sk_xs + (size_t)(2 * warp + rr) * K);
@@ -153,7 +158,7 @@ skinny_linear_kernel(const SkinnyParams p) {
 #pragma unroll
             for (int i = 0; i < SK_KMAX / 128; ++i)
                 if (i < KI) {
-                    const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+                    const float4 g = g4[i * 32 + lane], b = b4[i * 32 + lane];
                     float4 o;
                     o.x = v[i].x * rstd * g.x + b.x; o.y = v[i].y * rstd * g.y + b.y;
                     o.z = v[i].z * rstd * g.z + b.z; o.w = v[i].w * rstd * g.w + b.w;
@@ -410,47 +415,62 @@ head_xattn_kernel(const float* __restrict__ feats, const float* __restrict__ u, 
             if (*is_last) {       // this segment completed the crop: merge the segments in chunk order
                 __threadfence();
                 if (tid < 8) {
-                    float M = -INFINITY, L = 0.f;
-#pragma unroll 1
+                    // all 24 (m, l) values of the head's 12 chunk slots in flight at once: as two rolled loops of dependent
+                    // L2 reads this was ~16 us of serial latency on 8 threads at the very end of the kernel
+                    float mv[XA_NCH], lv[XA_NCH];
+#pragma unroll
                     for (int s = 0; s < XA_NCH; ++s) {
                         const int idx = b * XA_NCH + s;
                         const int cta = (int)(((long long)idx * G + items - 1) / items);
                         const bool start = PER_CHUNK || s == 0 || (cta < G && xa_range_start(cta, items, G) == idx);
-                        const float m = start ? __ldcg(ml + ((size_t)idx * 8 + tid) * 2) : -INFINITY;
-                        wsm[s * 8 + tid] = m;
-                        M = fmaxf(M, m);
+                        const float2 v = __ldcg(reinterpret_cast<const float2*>(ml + ((size_t)idx * 8 + tid) * 2));
+                        mv[s] = start ? v.x : -INFINITY;
+                        lv[s] = v.y;
                     }
-#pragma unroll 1
+                    float M = -INFINITY, L = 0.f;
+#pragma unroll
+                    for (int s = 0; s < XA_NCH; ++s) M = fmaxf(M, mv[s]);
+                    float ev[XA_NCH];
+#pragma unroll
                     for (int s = 0; s < XA_NCH; ++s) {
-                        const float m = wsm[s * 8 + tid];
-                        const float e = m == -INFINITY ? 0.f : expf(m - M);
-                        if (e != 0.f) L = fmaf(e, __ldcg(ml + ((size_t)(b * XA_NCH + s) * 8 + tid) * 2 + 1), L);
-                        wsm[s * 8 + tid] = m == -INFINITY ? -1.f : e;          // -1 marks "no segment starts here"
+                        ev[s] = mv[s] == -INFINITY ? 0.f : expf(mv[s] - M);
+                        if (ev[s] != 0.f) L = fmaf(ev[s], lv[s], L);
                     }
                     const float inv = 1.0f / L;
-#pragma unroll 1
-                    for (int s = 0; s < XA_NCH; ++s) if (wsm[s * 8 + tid] >= 0.f) wsm[s * 8 + tid] *= inv;
+#pragma unroll
+                    for (int s = 0; s < XA_NCH; ++s) wsm[s * 8 + tid] = mv[s] == -INFINITY ? -1.f : ev[s] * inv;   // -1: no segment starts here
                 }
                 if (tid == 0) ticket[b] = 0u;
                 __syncthreads();
+                // Two heads at a time with all 12 segments' loads in flight (24 independent L2 reads per thread): the merge is
+                // the serial tail of the kernel when a crop's segments come from 12 different CTAs (few crops), and a loop over
+                // the segments with 8 loads each was 12 dependent round trips.  Same summation order per head as before.
                 const float4* src = reinterpret_cast<const float4*>(part + (size_t)b * XA_NCH * 8 * 1280) + tid;
-                float4 o[8];
-#pragma unroll
-                for (int h = 0; h < 8; ++h) o[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4* dstp = reinterpret_cast<float4*>(pooled + (size_t)b * 8 * 1280) + tid;
 #pragma unroll 1
-                for (int s = 0; s < XA_NCH; ++s) {
-                    if (wsm[s * 8] < 0.f) continue;                              // block-uniform
+                for (int h0 = 0; h0 < 8; h0 += 2) {
+                    float4 v[XA_NCH][2];
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const float4 v = __ldcg(src + ((size_t)s * 8 + h) * 320);
-                        const float w = wsm[s * 8 + h];
-                        o[h].x = fmaf(w, v.x, o[h].x); o[h].y = fmaf(w, v.y, o[h].y);
-                        o[h].z = fmaf(w, v.z, o[h].z); o[h].w = fmaf(w, v.w, o[h].w);
+                    for (int s = 0; s < XA_NCH; ++s) {
+                        const bool on = wsm[s * 8] >= 0.f;                       // block-uniform: a segment starts at chunk s
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh)
+                            v[s][hh] = on ? __ldcg(src + ((size_t)s * 8 + h0 + hh) * 320) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int s = 0; s < XA_NCH; ++s) {
+                            const float w = wsm[s * 8 + h0 + hh];
+                            if (w >= 0.f) {                                      // block-uniform (same segments for every head)
+                                o.x = fmaf(w, v[s][hh].x, o.x); o.y = fmaf(w, v[s][hh].y, o.y);
+                                o.z = fmaf(w, v[s][hh].z, o.z); o.w = fmaf(w, v[s][hh].w, o.w);
+                            }
+                        }
+                        dstp[(h0 + hh) * 320] = o;
                     }
                 }
-                float4* dstp = reinterpret_cast<float4*>(pooled + (size_t)b * 8 * 1280) + tid;
-#pragma unroll
-                for (int h = 0; h < 8; ++h) dstp[h * 320] = o[h];
             }
             seg_n = 0;
         }
