@@ -84,9 +84,12 @@ __device__ __forceinline__ void sk_cp_async_wait(int pending) {   // cp.async.wa
     }
 }
 
-template <int CPW, int EPI, bool LNF>
+// RT = rows of the tile that are computed (4, 8 or 16): with a handful of crops (video frames) the other rows of the 16-row
+// tile are padding, and every row costs a shared-memory read of the whole K per warp.
+template <int CPW, int EPI, bool LNF, int RT = SK_ROWS>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 skinny_linear_kernel(const SkinnyParams p) {
+    static_assert(RT == 4 || RT == 8 || RT == 16, "row tile");
     ptx::pdl_prologue();
     extern __shared__ __align__(16) float sk_smem[];            // X tile [SK_ROWS][K], then the W slots
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +135,20 @@ skinny_linear_kernel(const SkinnyParams p) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // bias and residual of the thread's output elements: issued now, consumed in the epilogue (lanes i and i + 16 own row i;
+    // read at the end they were one more exposed L2 round trip per kernel)
+    float bias_r[CPW], resid_r[CPW];
+    {
+        const int r = lane & 15;
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int n = n0 + c;
+            const bool mine = lane < 16 && r < rows && n < p.N;
+            bias_r[c] = (mine && p.bias) ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
+            resid_r[c] = 0.f;
+            if constexpr (EPI == SK_RESID) { if (mine) resid_r[c] = p.R[(size_t)(b0 + r) * p.ldr + n]; }
+        }
+    }
     sk_cp_async_wait(NG);                                       // the X tile has landed
     __syncthreads();
     if constexpr (LNF) {
@@ -140,6 +157,7 @@ skinny_linear_kernel(const SkinnyParams p) {
         const float4* b4 = reinterpret_cast<const float4*>(sk_ln + K);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
+            if (2 * warp + rr >= RT) continue;                  // padding rows of a small batch (warp-uniform)
             float4* xr = reinterpret_cast<float4*>(sk_xs + (size_t)(2 * warp + rr) * K);
             float4 v[SK_KMAX / 128];
             float s = 0.f;
@@ -167,7 +185,7 @@ skinny_linear_kernel(const SkinnyParams p) {
         }
         __syncthreads();
     }
-    float acc[CPW][SK_ROWS];
+    float acc[CPW][SK_ROWS];                                    // rows >= RT stay zero
 #pragma unroll
     for (int c = 0; c < CPW; ++c)
 #pragma unroll
@@ -183,7 +201,7 @@ skinny_linear_kernel(const SkinnyParams p) {
 #pragma unroll
                 for (int c = 0; c < CPW; ++c) wc[c] = wslot[(i * CPW + c) * 32];
 #pragma unroll
-                for (int r = 0; r < SK_ROWS; ++r) {
+                for (int r = 0; r < RT; ++r) {
                     const float4 x = xs4[(size_t)r * K4 + i * 32];
 #pragma unroll
                     for (int c = 0; c < CPW; ++c)
@@ -198,10 +216,9 @@ skinny_linear_kernel(const SkinnyParams p) {
         float v = warp_transpose_reduce16(acc[c], lane);        // lanes i, i + 16: row i
         const int n = n0 + c;
         if (lane < 16 && r < rows && n < p.N) {
-            const float bias = p.bias ? __ldg(p.bias + z * p.bias_bs + n) : 0.f;
-            v = v * p.scale + bias;
+            v = v * p.scale + bias_r[c];
             if constexpr (EPI == SK_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-            if constexpr (EPI == SK_RESID) v += p.R[(size_t)(b0 + r) * p.ldr + n];
+            if constexpr (EPI == SK_RESID) v += resid_r[c];
             Y[(size_t)(b0 + r) * p.ldy + n] = v;
         }
     }

@@ -337,11 +337,11 @@ void launch_ln(const float* x, const float* g, const float* b, OutT* y, int rows
     launch_pdl(layernorm_kernel<V, OutT>, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, y, rows, eps);
 }
 
-template <int CPW, bool LNF>
+template <int CPW, bool LNF, int RT = SK_ROWS>
 void launch_skinny_epi(int epi, dim3 grid, size_t smem, cudaStream_t s, const SkinnyParams& p) {
-    if (epi == SK_NONE) launch_pdl(skinny_linear_kernel<CPW, SK_NONE, LNF>, grid, dim3(SK_WARPS * 32), smem, s, p);
-    else if (epi == SK_GELU) launch_pdl(skinny_linear_kernel<CPW, SK_GELU, LNF>, grid, dim3(SK_WARPS * 32), smem, s, p);
-    else launch_pdl(skinny_linear_kernel<CPW, SK_RESID, LNF>, grid, dim3(SK_WARPS * 32), smem, s, p);
+    if (epi == SK_NONE) launch_pdl(skinny_linear_kernel<CPW, SK_NONE, LNF, RT>, grid, dim3(SK_WARPS * 32), smem, s, p);
+    else if (epi == SK_GELU) launch_pdl(skinny_linear_kernel<CPW, SK_GELU, LNF, RT>, grid, dim3(SK_WARPS * 32), smem, s, p);
+    else launch_pdl(skinny_linear_kernel<CPW, SK_RESID, LNF, RT>, grid, dim3(SK_WARPS * 32), smem, s, p);
 }
 
 // ln_g != nullptr: the input rows are LayerNorm-ed (eps 1e-5, the decoder's PreNorm) inside the kernel
@@ -366,6 +366,8 @@ cudaError_t launch_skinny(int num_sms, int epi, const float* X, int ldx, long lo
     const bool lnf = ln_g != nullptr;
     if (cpw == 4) { if (lnf) launch_skinny_epi<4, true>(epi, grid, smem, s, p); else launch_skinny_epi<4, false>(epi, grid, smem, s, p); }
     else if (cpw == 2) { if (lnf) launch_skinny_epi<2, true>(epi, grid, smem, s, p); else launch_skinny_epi<2, false>(epi, grid, smem, s, p); }
+    else if (B <= 4) { if (lnf) launch_skinny_epi<1, true, 4>(epi, grid, smem, s, p); else launch_skinny_epi<1, false, 4>(epi, grid, smem, s, p); }
+    else if (B <= 8) { if (lnf) launch_skinny_epi<1, true, 8>(epi, grid, smem, s, p); else launch_skinny_epi<1, false, 8>(epi, grid, smem, s, p); }
     else { if (lnf) launch_skinny_epi<1, true>(epi, grid, smem, s, p); else launch_skinny_epi<1, false>(epi, grid, smem, s, p); }
     return cudaGetLastError();
 }
@@ -662,6 +664,12 @@ int hm_create(hm_ctx** out, int device_ordinal, const hm_config* cfg) {
     sk_attr(skinny_linear_kernel<CPW, SK_RESID, false>); sk_attr(skinny_linear_kernel<CPW, SK_RESID, true>);
     SK_ATTR_ALL(1) SK_ATTR_ALL(2) SK_ATTR_ALL(4)
 #undef SK_ATTR_ALL
+#define SK_ATTR_RT(RT)                                                                                                \
+    sk_attr(skinny_linear_kernel<1, SK_NONE, false, RT>); sk_attr(skinny_linear_kernel<1, SK_NONE, true, RT>);       \
+    sk_attr(skinny_linear_kernel<1, SK_GELU, false, RT>); sk_attr(skinny_linear_kernel<1, SK_GELU, true, RT>);       \
+    sk_attr(skinny_linear_kernel<1, SK_RESID, false, RT>); sk_attr(skinny_linear_kernel<1, SK_RESID, true, RT>);
+    SK_ATTR_RT(4) SK_ATTR_RT(8)
+#undef SK_ATTR_RT
     sk_ok = sk_ok && cudaFuncSetAttribute(head_xattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XA_SMEM_BYTES) == cudaSuccess &&
             cudaFuncSetAttribute(head_xattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XA_SMEM_BYTES) == cudaSuccess;
     if (!sk_ok ||
