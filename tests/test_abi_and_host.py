@@ -225,3 +225,23 @@ def test_npy_record_layout(tmp_path):
     # axis-angle round trip through cv2.Rodrigues
     import cv2
     assert np.allclose(cv2.Rodrigues(d['pose_global'])[0], R[0, 0].numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize('B', [1, 2, 3, 5, 7, 8, 64])
+def test_graph_output_buffer_fields_are_aligned(B):
+    """The packed output buffer of a CUDA graph: every field 64-byte aligned for every batch size, fields disjoint, shapes as
+    hm_outputs expects.  (With tightly packed fields an odd batch put pred_vertices 4 bytes off and hm_mano_lbs silently took its
+    three-kernel path: same tolerances, different bits.)"""
+    from hamer_yolo_b200.hamer import Engine
+    flat = torch.zeros(Engine._flat_floats(B), dtype=torch.float32)
+    views = Engine._views(Engine, flat, B)
+    spans = []
+    for name, shp in Engine._FIELDS:
+        v = views[name]
+        assert tuple(v.shape) == (B, *shp) and v.is_contiguous()
+        off = (v.data_ptr() - flat.data_ptr())
+        assert off % 64 == 0, (name, off)
+        spans.append((off, off + v.numel() * 4))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert spans[-1][1] <= flat.numel() * 4
