@@ -26,7 +26,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // (vit.py:335); nn.LayerNorm(1024, eps=1e-5) in the decoder's PreNorm (pose_transformer.py:30).
 // D = 32 * 4 * V elements.  OutT = __nv_bfloat16 (feeds a GEMM) or float (last_norm / decoder).
 // ------------------------------------------------------------------------------------------------
-template <int V, typename OutT>
+// EARLY_GB: gamma / beta are requested together with the row (80 more registers) instead of after the statistics - with a
+// few hundred rows (video frames) the kernel is one latency chain and that second trip to L2 is a fifth of it; with
+// thousands of rows occupancy matters more and the late loads hit L1.
+template <int V, typename OutT, bool EARLY_GB = false>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, OutT* __restrict__ y, int rows, float eps) {
@@ -36,12 +39,32 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
     float4 v[V];
+    float4 ge[EARLY_GB ? V : 1], be[EARLY_GB ? V : 1];
+    if constexpr (EARLY_GB) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {       // volatile + memory clobber: ptxas otherwise sinks these loads back to their use
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "l"(xr + i * 32 + lane) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ge[i].x), "=f"(ge[i].y), "=f"(ge[i].z), "=f"(ge[i].w) : "l"(g4 + i * 32 + lane) : "memory");
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(be[i].x), "=f"(be[i].y), "=f"(be[i].z), "=f"(be[i].w) : "l"(b4 + i * 32 + lane) : "memory");
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = xr[i * 32 + lane];
+    }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        v[i] = xr[i * 32 + lane];
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    if constexpr (EARLY_GB) {               // a data dependence ptxas cannot schedule around: the loads above stay above
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) t += ge[i].x + be[i].x;
+        s = fmaf(t, 0.0f, s);               // (adds zero: only t's availability before the reductions matters)
     }
     const float mean = warp_sum(s) * (1.0f / D);
     float q = 0.f;
@@ -51,11 +74,11 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-    const float4* g4 = reinterpret_cast<const float4*>(gamma);
-    const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+        float4 g, b;
+        if constexpr (EARLY_GB) { g = ge[i]; b = be[i]; }
+        else { g = __ldg(g4 + i * 32 + lane); b = __ldg(b4 + i * 32 + lane); }
         float4 o;
         o.x = v[i].x * rstd * g.x + b.x;
         o.y = v[i].y * rstd * g.y + b.y;

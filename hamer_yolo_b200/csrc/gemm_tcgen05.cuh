@@ -211,6 +211,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if constexpr (CTA_GROUP == 2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // The W operand is constant: its tiles for the first k-blocks of this CTA's first item are requested BEFORE waiting for the
+    // previous kernel (under programmatic dependent launch - small batches - this CTA is often resident while the previous,
+    // smaller kernel is still running, and the weight stream of a few-crop GEMM is most of its traffic).  The A tiles of
+    // the same stages follow after the wait; both complete on the stage's full barrier.
+    int pre_stages = 0;
+    if (warp == 0 && lane == 0 && worker < num_items) {
+        const GemmItem wi = gemm_item(worker, full_tiles, ksplit, num_k);
+        const int n_blk = wi.tile % n_blocks;
+        const int n0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
+        pre_stages = wi.kb1 - wi.kb0 < STAGES ? wi.kb1 - wi.kb0 : STAGES;
+        for (int i = 0; i < pre_stages; ++i) {           // every slot is free at kernel start
+            if constexpr (CTA_GROUP == 1) {
+                ptx::mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+                ptx::tma_load_2d(smem_b + i * Cfg::B_BYTES, &tmap_b, &full_bar[i], (wi.kb0 + i) * GEMM_BK, n0);
+            } else {
+                if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[i], 2 * Cfg::STAGE_BYTES);
+                ptx::tma_load_2d_2sm(smem_b + i * Cfg::B_BYTES, &tmap_b, &full_bar[i], (wi.kb0 + i) * GEMM_BK, n0);
+            }
+        }
+    }
     ptx::griddep_wait();                // barriers / TMEM / tensor maps are set up; now wait for the previous kernel's data
 
     if (warp == 0) {
@@ -225,6 +245,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 const int n0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     const int ka = (p.a_kwrap > 0 && kb >= p.a_kwrap) ? kb - p.a_kwrap : kb;
+                    if (item == worker && kb - wi.kb0 < pre_stages) {
+                        // the stage's barrier is armed and its W tile already on the way: only the A tile is missing
+                        if constexpr (CTA_GROUP == 1)
+                            ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], ka * GEMM_BK, m0);
+                        else
+                            ptx::tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], ka * GEMM_BK, m0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if constexpr (CTA_GROUP == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -299,6 +328,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int row0 = m_blk * tile_m + (int)cta_rank * GEMM_BM + quad * 32;
             const int row = row0 + lane;
             const int col0 = n_blk * BN + part * COLS_PER_WARP;
+            // the bias of the warp's columns into L1 while the MMAs of the tile are still running: read behind
+            // tcgen05.wait::ld it is an exposed trip to L2 per chunk (one tile per CTA at small batches: nothing hides it)
+            if (lane < COLS_PER_WARP / 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + col0 + lane * 32));
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) +

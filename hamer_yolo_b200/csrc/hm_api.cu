@@ -334,7 +334,8 @@ void invert_affine(const double M[6], double out[6]) {
 template <int V, typename OutT>
 void launch_ln(const float* x, const float* g, const float* b, OutT* y, int rows, float eps,
                cudaStream_t s) {
-    launch_pdl(layernorm_kernel<V, OutT>, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, y, rows, eps);
+    if (rows <= 24 * TOK) launch_pdl(layernorm_kernel<V, OutT, true>, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, y, rows, eps);
+    else launch_pdl(layernorm_kernel<V, OutT>, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, y, rows, eps);
 }
 
 template <int CPW, bool LNF, int RT = SK_ROWS>
