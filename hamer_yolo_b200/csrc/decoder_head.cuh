@@ -90,7 +90,7 @@ template <int CPW, int EPI, bool LNF, int RT = SK_ROWS>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 skinny_linear_kernel(const SkinnyParams p) {
     static_assert(RT == 4 || RT == 8 || RT == 16, "row tile");
-    ptx::pdl_prologue();
+    ptx::griddep_launch_dependents();   // (the wait for the previous kernel comes after the weight copies are in flight)
     extern __shared__ __align__(16) float sk_smem[];            // X tile [SK_ROWS][K], then the W slots
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = (blockIdx.x * SK_WARPS + warp) * CPW;
@@ -107,19 +107,15 @@ skinny_linear_kernel(const SkinnyParams p) {
     float4* wslot = reinterpret_cast<float4*>(sk_smem + (size_t)SK_ROWS * K) + (size_t)warp * (KI * CPW * 32) + lane;
 
     // Everything the block will read goes in flight at once (X tile 16 K floats, W 8 CPW K floats: up to 192 KB): the
-    // kernel is a latency chain otherwise (one block per SM, a handful of dependent round trips to L2 / HBM).
-    for (int e = threadIdx.x; e < SK_ROWS * K4; e += blockDim.x) {
-        const int r = e / K4, c = e - r * K4;
-        float* dst = sk_xs + (size_t)r * K + c * 4;
-        if (r < rows) sk_cp_async16(dst, X + (size_t)(b0 + r) * p.ldx + c * 4);
-        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // no predicates in the inner loop
-    }
+    // kernel is a latency chain otherwise (one block per SM, a handful of dependent round trips to L2 / HBM).  The
+    // weights and the LayerNorm parameters are constants, so their copies are issued BEFORE the wait for the previous
+    // kernel (programmatic dependent launch: this block is often resident while a smaller predecessor still runs); the
+    // activations follow after it, as the last copy group.
     float* sk_ln = sk_smem + (size_t)(SK_ROWS + SK_WARPS * CPW) * K;   // LNF: [gamma (K) | beta (K)], behind the W slots
-    if constexpr (LNF) {                                        // the LayerNorm parameters ride with the X tile (same copy group):
-        for (int e = threadIdx.x; e < 2 * K4; e += blockDim.x)  // read from global inside the normalisation they were an exposed L2 trip
+    if constexpr (LNF) {
+        for (int e = threadIdx.x; e < 2 * K4; e += blockDim.x)
             sk_cp_async16(sk_ln + e * 4, (e < K4 ? p.ln_g : p.ln_b - K) + e * 4);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     const float* wrow[CPW];                                     // columns past N re-read the last valid row (results dropped)
 #pragma unroll
     for (int c = 0; c < CPW; ++c) wrow[c] = W + (size_t)min(n0 + c, p.N - 1) * K + lane * 4;
@@ -135,6 +131,14 @@ skinny_linear_kernel(const SkinnyParams p) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    ptx::griddep_wait();
+    for (int e = threadIdx.x; e < SK_ROWS * K4; e += blockDim.x) {
+        const int r = e / K4, c = e - r * K4;
+        float* dst = sk_xs + (size_t)r * K + c * 4;
+        if (r < rows) sk_cp_async16(dst, X + (size_t)(b0 + r) * p.ldx + c * 4);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // no predicates in the inner loop
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // bias and residual of the thread's output elements: issued now, consumed in the epilogue (lanes i and i + 16 own row i;
     // read at the end they were one more exposed L2 round trip per kernel)
     float bias_r[CPW], resid_r[CPW];
@@ -149,7 +153,7 @@ skinny_linear_kernel(const SkinnyParams p) {
             if constexpr (EPI == SK_RESID) { if (mine) resid_r[c] = p.R[(size_t)(b0 + r) * p.ldr + n]; }
         }
     }
-    sk_cp_async_wait(NG);                                       // the X tile has landed
+    sk_cp_async_wait(0);                                        // the X tile (the last group, so everything) has landed
     __syncthreads();
     if constexpr (LNF) {
         // PreNorm: rows 2 warp, 2 warp + 1 of the staged tile, two-pass statistics (same arithmetic as layernorm_kernel)
@@ -192,7 +196,7 @@ skinny_linear_kernel(const SkinnyParams p) {
         for (int r = 0; r < SK_ROWS; ++r) acc[c][r] = 0.f;
     const float4* xs4 = reinterpret_cast<const float4*>(sk_xs) + lane;
     for (int g = 0; g < NG; ++g) {
-        sk_cp_async_wait(NG - 1 - g);                           // W group g has landed (groups complete in order)
+        // (every copy group has completed by now: X was the last one)
 #pragma unroll
         for (int ii = 0; ii < 2; ++ii) {
             const int i = 2 * g + ii;
