@@ -35,3 +35,21 @@ def test_scale_coords_round_trip():
     assert dets[0][0] == 'right' and dets[1][0] == 'left'
     assert dets[0][1] == [301.0, 115.0, 902.0, 567.0]         # (x - 0) * 3, (y - 12) * 3, rounded half to even
     assert dets[1][1] == [0.0, 0.0, 1920.0, 1080.0]           # clipped to the frame
+
+
+def test_hm_letterbox_shape_matches_the_reference_geometry():
+    """hm_letterbox_shape is pure host arithmetic of libhamer_b200.so (no GPU): the padded output shape of
+    letterbox(img0, new_size, stride, auto=True) (yolo/yolov7/utils/datasets.py:999-1030) for a sweep of frame sizes."""
+    import ctypes as C
+    from hamer_yolo_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    cases = [(1080, 1920), (480, 640), (720, 1280), (2160, 3840), (100, 100), (37, 1000), (1000, 37), (641, 641), (1, 1)]
+    cases += [(int(rng.integers(8, 2200)), int(rng.integers(8, 4000))) for _ in range(60)]
+    for new_size, stride in ((640, 32), (960, 32), (416, 64)):
+        for h, w in cases:
+            oh, ow = C.c_int32(), C.c_int32()
+            rc = lib.hm_letterbox_shape(h, w, new_size, stride, C.byref(oh), C.byref(ow))
+            img = np.zeros((h, w, 3), np.uint8)
+            ref = ol.letterbox(img, new_size, stride=stride)[0].shape[:2]
+            assert rc == 0 and (oh.value, ow.value) == ref, (h, w, new_size, stride, (oh.value, ow.value), ref)
